@@ -1,0 +1,300 @@
+// abi.cu -- the extern "C" boundary declared in include/svdlas2.h.  Exceptions never cross it: every entry
+// point maps las2::Error (and anything else) to a status code and a thread-local message.
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "las2.hpp"
+#include "spmv.cuh"
+
+using namespace las2;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        g_last_error.clear();
+        f();
+        return SVDLAS2_OK;
+    } catch (const Error &e) {
+        cudaGetLastError(); // clear a sticky-free error state
+        return fail(e.code, e.what());
+    } catch (const std::bad_alloc &) {
+        return fail(SVDLAS2_ERR_ALLOC, "host allocation failed");
+    } catch (const std::exception &e) {
+        return fail(SVDLAS2_ERR_CUDA, std::string("unexpected: ") + e.what());
+    } catch (...) {
+        return fail(SVDLAS2_ERR_CUDA, "unexpected exception");
+    }
+}
+
+double wall_now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+void select_device(int device, Operator &op) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw Error(SVDLAS2_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU fallback): ") +
+                                          cudaGetErrorString(e));
+    }
+    if (device < 0) LAS2_CUDA(cudaGetDevice(&device));
+    if (device >= count) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "device index out of range");
+    LAS2_CUDA(cudaSetDevice(device));
+    op.device = device;
+    LAS2_CUDA(cudaStreamCreateWithFlags(&op.stream, cudaStreamNonBlocking));
+}
+
+Operator *create_operator(int format, u64 nrows, u64 ncols, u64 nnz, const u64 *a, const u64 *b, const double *values,
+                          int device) {
+    if (format != SVDLAS2_FMT_CSR && format != SVDLAS2_FMT_CSC && format != SVDLAS2_FMT_COO)
+        throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "unknown sparse format");
+    std::unique_ptr<Operator> op(new Operator());
+    select_device(device, *op);
+    const double t0 = wall_now();
+    op->a_rows = nrows; op->a_cols = ncols; op->nnz_global = nnz;
+    // If the matrix is wide, the SVD is computed on its transpose (src/lib.rs:606)
+    op->transposed = (double)ncols >= ((double)nrows * 1.2);
+    op->M_global = op->M = op->transposed ? ncols : nrows;
+    op->N = op->transposed ? nrows : ncols;
+    HostSparse A{format, nrows, ncols, nnz, a, b, values};
+    build_operator(A, op->transposed, op->stream, op->B, op->BT, op->upload);
+    op->t_upload = wall_now() - t0;
+    return op.release();
+}
+
+svdlas2_result *new_result() {
+    svdlas2_result *r = (svdlas2_result *)std::calloc(1, sizeof(svdlas2_result));
+    if (!r) throw std::bad_alloc();
+    return r;
+}
+
+int one_shot(int format, u64 nrows, u64 ncols, u64 nnz, const u64 *a, const u64 *b, const double *values,
+             u64 dimensions, u64 iterations, const double end_interval[2], double kappa, uint32_t seed,
+             svdlas2_result **out) {
+    if (!out) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!end_interval) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "end_interval is null");
+    svdlas2_result *res = nullptr;
+    int rc = guarded([&] {
+        const double t0 = wall_now();
+        res = new_result();
+        // the reference rejects dimensions < 2 before touching the matrix (src/lib.rs:583-600)
+        const u64 mn = nrows < ncols ? nrows : ncols;
+        u64 dims = (dimensions == 0 || dimensions > mn) ? mn : dimensions;
+        if (dims < 2) throw Error(SVDLAS2_ERR_LAS2, "svdLAS2: insufficient dimensions: " + std::to_string(dims));
+        std::unique_ptr<Operator> op(create_operator(format, nrows, ncols, nnz, a, b, values, -1));
+        solve(*op, dimensions, iterations, end_interval, kappa, seed, res);
+        res->profile.t_total = wall_now() - t0;
+    });
+    if (rc != SVDLAS2_OK) {
+        svdlas2_free(res);
+        return rc;
+    }
+    *out = res;
+    return rc;
+}
+
+} // namespace
+
+extern "C" {
+
+int svdlas2_abi_version(void) { return SVDLAS2_ABI_VERSION; }
+
+const char *svdlas2_last_error(void) { return g_last_error.c_str(); }
+
+int svdlas2_csr(uint64_t nrows, uint64_t ncols, uint64_t nnz, const uint64_t *row_offsets, const uint64_t *col_indices,
+                const double *values, uint64_t dimensions, uint64_t iterations, const double end_interval[2],
+                double kappa, uint32_t random_seed, svdlas2_result **out) {
+    return one_shot(SVDLAS2_FMT_CSR, nrows, ncols, nnz, row_offsets, col_indices, values, dimensions, iterations,
+                    end_interval, kappa, random_seed, out);
+}
+
+int svdlas2_csc(uint64_t nrows, uint64_t ncols, uint64_t nnz, const uint64_t *col_offsets, const uint64_t *row_indices,
+                const double *values, uint64_t dimensions, uint64_t iterations, const double end_interval[2],
+                double kappa, uint32_t random_seed, svdlas2_result **out) {
+    return one_shot(SVDLAS2_FMT_CSC, nrows, ncols, nnz, col_offsets, row_indices, values, dimensions, iterations,
+                    end_interval, kappa, random_seed, out);
+}
+
+int svdlas2_coo(uint64_t nrows, uint64_t ncols, uint64_t nnz, const uint64_t *row_indices, const uint64_t *col_indices,
+                const double *values, uint64_t dimensions, uint64_t iterations, const double end_interval[2],
+                double kappa, uint32_t random_seed, svdlas2_result **out) {
+    return one_shot(SVDLAS2_FMT_COO, nrows, ncols, nnz, row_indices, col_indices, values, dimensions, iterations,
+                    end_interval, kappa, random_seed, out);
+}
+
+void svdlas2_free(svdlas2_result *r) {
+    if (!r) return;
+    std::free(r->ut); std::free(r->s); std::free(r->vt);
+    std::free(r->alf); std::free(r->bet); std::free(r->ritz); std::free(r->bnd);
+    std::free(r);
+}
+
+int svdlas2_operator_create(int format, uint64_t nrows, uint64_t ncols, uint64_t nnz, const uint64_t *a,
+                            const uint64_t *b, const double *values, int device, svdlas2_operator **out) {
+    if (!out) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "op is null");
+    *out = nullptr;
+    return guarded([&] { *out = reinterpret_cast<svdlas2_operator *>(create_operator(format, nrows, ncols, nnz, a, b, values, device)); });
+}
+
+void svdlas2_operator_destroy(svdlas2_operator *op_) {
+    Operator *op = reinterpret_cast<Operator *>(op_);
+    if (!op) return;
+    cudaSetDevice(op->device);
+    if (op->stream) cudaStreamSynchronize(op->stream);
+    delete op;
+}
+
+int svdlas2_operator_solve(svdlas2_operator *op_, uint64_t dimensions, uint64_t iterations, const double end_interval[2],
+                           double kappa, uint32_t random_seed, svdlas2_result **out) {
+    Operator *op = reinterpret_cast<Operator *>(op_);
+    if (!op || !out || !end_interval) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    svdlas2_result *res = nullptr;
+    int rc = guarded([&] {
+        res = new_result();
+        solve(*op, dimensions, iterations, end_interval, kappa, random_seed, res);
+    });
+    if (rc != SVDLAS2_OK) {
+        svdlas2_free(res);
+        return rc;
+    }
+    *out = res;
+    return rc;
+}
+
+int svdlas2_operator_shape(const svdlas2_operator *op_, uint64_t *m, uint64_t *n, uint64_t *nnz, int *transposed) {
+    const Operator *op = reinterpret_cast<const Operator *>(op_);
+    if (!op) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null operator");
+    if (m) *m = op->M;
+    if (n) *n = op->N;
+    if (nnz) *nnz = op->B.nnz;
+    if (transposed) *transposed = op->transposed ? 1 : 0;
+    return SVDLAS2_OK;
+}
+
+int svdlas2_operator_opa(svdlas2_operator *op_, const double *x, double *y, int transposed) {
+    Operator *op = reinterpret_cast<Operator *>(op_);
+    if (!op || !x || !y) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        if (op->comm) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "opa is not available on a sharded operator");
+        LAS2_CUDA(cudaSetDevice(op->device));
+        // y = A x or A' x ; with B = A (not transposed) or B = A' (transposed): A = B or B'
+        const bool use_b = (transposed != 0) == op->transposed; // A x -> B x when !op.transposed ; A'x -> B x when op.transposed
+        const DeviceCsr &Mx = use_b ? op->B : op->BT;
+        DevBuf<double> dx(Mx.cols ? Mx.cols : 1), dy(Mx.rows ? Mx.rows : 1);
+        LAS2_CUDA(cudaMemcpyAsync(dx.get(), x, Mx.cols * sizeof(double), cudaMemcpyHostToDevice, op->stream));
+        spmv(Mx, dx.get(), dy.get(), op->stream);
+        LAS2_CUDA(cudaMemcpyAsync(y, dy.get(), Mx.rows * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
+        LAS2_CUDA(cudaStreamSynchronize(op->stream));
+    });
+}
+
+int svdlas2_operator_opb(svdlas2_operator *op_, const double *x, double *y) {
+    Operator *op = reinterpret_cast<Operator *>(op_);
+    if (!op || !x || !y) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        LAS2_CUDA(cudaSetDevice(op->device));
+        DevBuf<double> dx(op->N ? op->N : 1), dy(op->N ? op->N : 1), dt(op->M ? op->M : 1);
+        LAS2_CUDA(cudaMemcpyAsync(dx.get(), x, op->N * sizeof(double), cudaMemcpyHostToDevice, op->stream));
+        op->opb(dx.get(), dy.get(), dt.get(), nullptr);
+        LAS2_CUDA(cudaMemcpyAsync(y, dy.get(), op->N * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
+        LAS2_CUDA(cudaStreamSynchronize(op->stream));
+    });
+}
+
+int svdlas2_operator_time_opb(svdlas2_operator *op_, int reps, int flush_l2, double *ms_per_opb, double *ms_spmv_b,
+                              double *ms_spmv_bt) {
+    Operator *op = reinterpret_cast<Operator *>(op_);
+    if (!op || reps < 1) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        LAS2_CUDA(cudaSetDevice(op->device));
+        cudaStream_t s = op->stream;
+        DevBuf<double> dx(op->N ? op->N : 1), dy(op->N ? op->N : 1), dt(op->M ? op->M : 1);
+        std::vector<double> hx(op->N);
+        for (u64 i = 0; i < op->N; i++) hx[i] = 1.0 / (double)(1 + (i % 97));
+        LAS2_CUDA(cudaMemcpyAsync(dx.get(), hx.data(), op->N * sizeof(double), cudaMemcpyHostToDevice, s));
+        const size_t flush_bytes = (size_t)256 << 20; // > 126 MB L2
+        if (flush_l2 && op->l2_flush.size() < flush_bytes) op->l2_flush.alloc(flush_bytes);
+        cudaEvent_t e0, e1, e2;
+        LAS2_CUDA(cudaEventCreate(&e0)); LAS2_CUDA(cudaEventCreate(&e1)); LAS2_CUDA(cudaEventCreate(&e2));
+        for (int w = 0; w < 3; w++) op->opb(dx.get(), dy.get(), dt.get(), nullptr); // warm-up
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        double tb = 0.0, tbt = 0.0;
+        for (int i = 0; i < reps; i++) {
+            if (flush_l2) LAS2_CUDA(cudaMemsetAsync(op->l2_flush.get(), i & 0xff, flush_bytes, s));
+            LAS2_CUDA(cudaEventRecord(e0, s));
+            spmv(op->B, dx.get(), dt.get(), s);
+            LAS2_CUDA(cudaEventRecord(e1, s));
+            spmv(op->BT, dt.get(), dy.get(), s);
+            if (op->comm) op->comm->allreduce_sum(dy.get(), op->N, s);
+            LAS2_CUDA(cudaEventRecord(e2, s));
+            LAS2_CUDA(cudaStreamSynchronize(s));
+            float a = 0.f, b = 0.f;
+            LAS2_CUDA(cudaEventElapsedTime(&a, e0, e1));
+            LAS2_CUDA(cudaEventElapsedTime(&b, e1, e2));
+            tb += a; tbt += b;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        if (ms_spmv_b) *ms_spmv_b = tb / reps;
+        if (ms_spmv_bt) *ms_spmv_bt = tbt / reps;
+        if (ms_per_opb) *ms_per_opb = (tb + tbt) / reps;
+    });
+}
+
+int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value) {
+    Operator *op = reinterpret_cast<Operator *>(op_);
+    if (!op || !knob) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
+    if (!std::strcmp(knob, "profile")) { op->profile = value != 0; return SVDLAS2_OK; }
+    if (!std::strcmp(knob, "spmv_variant")) { g_spmv_variant = (int)value; return SVDLAS2_OK; }
+    return fail(SVDLAS2_ERR_INVALID_ARGUMENT, std::string("unknown knob ") + knob);
+}
+
+int svdlas2_comm_unique_id(uint8_t id[SVDLAS2_COMM_ID_BYTES]) {
+    if (!id) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null id");
+    return guarded([&] { Comm::unique_id(id); });
+}
+
+int svdlas2_operator_create_shard(uint64_t m_global, uint64_t n, uint64_t row_begin, uint64_t row_end,
+                                  uint64_t local_nnz, const uint64_t *local_offsets, const uint64_t *local_indices,
+                                  const double *values, int b_is_a_transposed, uint64_t global_nnz, int rank,
+                                  int world_size, const uint8_t id[SVDLAS2_COMM_ID_BYTES], int device,
+                                  svdlas2_operator **out) {
+    if (!out) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "op is null");
+    *out = nullptr;
+    return guarded([&] {
+        if (row_end < row_begin || row_end > m_global) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "bad row range");
+        if (world_size > 1 && !id) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "null communicator id");
+        std::unique_ptr<Operator> op(new Operator());
+        select_device(device, *op);
+        const double t0 = wall_now();
+        op->transposed = b_is_a_transposed != 0;
+        op->a_rows = op->transposed ? n : m_global;
+        op->a_cols = op->transposed ? m_global : n;
+        op->nnz_global = global_nnz;
+        op->M_global = m_global;
+        op->M = row_end - row_begin;
+        op->row_begin = row_begin;
+        op->N = n;
+        build_operator_from_csr(op->M, n, local_nnz, local_offsets, local_indices, values, op->stream, op->B, op->BT,
+                                op->upload);
+        op->comm.reset(Comm::create(rank, world_size, id));
+        op->t_upload = wall_now() - t0;
+        *out = reinterpret_cast<svdlas2_operator *>(op.release());
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,95 @@
+// comm.cpp -- NCCL all-reduce over NVLink / NVSwitch for the row-sharded operator (see comm.hpp).
+// NCCL 2.28 is resolved at run time: first among the libraries already mapped into the process (the torch
+// wheel's libnccl.so.2 when the host program is Python), then by soname.
+#include "comm.hpp"
+
+#include <dlfcn.h>
+
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "util.cuh"
+
+namespace las2 {
+
+namespace {
+
+struct NcclUniqueId { char internal[128]; };
+using ncclComm_t = void *;
+enum { kNcclSum = 0, kNcclFloat64 = 8 };
+
+struct NcclApi {
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+NcclApi &api() {
+    static NcclApi a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) {
+            a.why = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return;
+        }
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+        a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+        if (!a.ok) a.why = "libnccl.so.2 lacks a required symbol";
+    });
+    return a;
+}
+
+void check(int rc, const char *what) {
+    if (rc != 0) throw Error(SVDLAS2_ERR_COMM, std::string(what) + ": " + api().GetErrorString(rc));
+}
+
+} // namespace
+
+void Comm::unique_id(uint8_t *id_out) {
+    NcclApi &a = api();
+    if (!a.ok) throw Error(SVDLAS2_ERR_COMM, a.why);
+    NcclUniqueId id;
+    check(a.GetUniqueId(&id), "ncclGetUniqueId");
+    static_assert(sizeof id == SVDLAS2_COMM_ID_BYTES, "id size");
+    std::memcpy(id_out, id.internal, sizeof id);
+}
+
+Comm *Comm::create(int rank, int world, const uint8_t *id_bytes) {
+    if (world < 1 || rank < 0 || rank >= world) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "bad rank / world_size");
+    Comm *c = new Comm();
+    c->rank_ = rank;
+    c->world_ = world;
+    if (world == 1) return c;
+    NcclApi &a = api();
+    if (!a.ok) { delete c; throw Error(SVDLAS2_ERR_COMM, a.why); }
+    NcclUniqueId id;
+    std::memcpy(id.internal, id_bytes, sizeof id);
+    ncclComm_t comm = nullptr;
+    int rc = a.CommInitRank(&comm, world, id, rank);
+    if (rc != 0) { delete c; check(rc, "ncclCommInitRank"); }
+    c->nccl_comm_ = comm;
+    return c;
+}
+
+Comm::~Comm() {
+    if (nccl_comm_) api().CommDestroy(nccl_comm_);
+}
+
+void Comm::allreduce_sum(double *buf, uint64_t n, cudaStream_t s) {
+    if (world_ == 1) return;
+    check(api().AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, nccl_comm_, s), "ncclAllReduce");
+}
+
+} // namespace las2

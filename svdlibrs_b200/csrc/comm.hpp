@@ -1,0 +1,29 @@
+// comm.hpp -- the one exchange step of the sharded operator: y = sum_g B_g'(B_g x), an
+// all-reduce of N doubles per svd_opb over NVLink.  One process per GPU; NCCL is loaded with dlopen so the
+// single-GPU library has no link-time dependency on it.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace las2 {
+
+class Comm {
+  public:
+    // id: SVDLAS2_COMM_ID_BYTES opaque bytes produced by unique_id() on rank 0 and broadcast by the caller
+    static Comm *create(int rank, int world, const uint8_t *id);
+    static void unique_id(uint8_t *id_out);
+    ~Comm();
+    int rank() const { return rank_; }
+    int world() const { return world_; }
+    // in-place sum over ranks, bit-identical result on every rank
+    void allreduce_sum(double *buf, uint64_t n, cudaStream_t s);
+
+  private:
+    Comm() = default;
+    int rank_ = 0, world_ = 1;
+    void *nccl_comm_ = nullptr;
+};
+
+} // namespace las2

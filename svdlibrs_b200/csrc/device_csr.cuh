@@ -1,0 +1,53 @@
+// device_csr.cuh -- the operator as it lives in HBM: CSR(B) and CSR(B') with 32-bit indices.
+//
+// Reference: the matrix is only ever touched through SMat::svd_opa (src/lib.rs:2035-2130), whose
+// `transposed` branch is a scatter loop.  Here the input is converted ONCE at upload into row-gather form
+// for both B and B' (north star "Input upload"), so neither half of svd_opb (:829-837) needs atomics.
+#pragma once
+
+#include "util.cuh"
+
+namespace las2 {
+
+// nnz-tile size of the streaming SpMV (see spmv.cu); value/index arrays are zero-padded to a multiple of it.
+constexpr u32 kSpmvTile = 2048;
+
+struct DeviceCsr {
+    u64 rows = 0, cols = 0, nnz = 0;
+    DevBuf<u32> off;    // rows + 1 row offsets
+    DevBuf<u32> idx;    // padded_nnz column indices (padding: index 0)
+    DevBuf<double> val; // padded_nnz values        (padding: 0.0)
+    u64 padded_nnz = 0;
+    // streaming-SpMV tile table: tile b covers nnz [b*kSpmvTile, (b+1)*kSpmvTile)
+    u32 num_tiles = 0;
+    DevBuf<u32> tile_row;  // num_tiles + 1: first row that ENDS after the tile's first nnz (tile_row[0] = 0)
+    DevBuf<double> carry;  // num_tiles: partial sum of the row that continues into the next tile
+    DevBuf<double> head;   // num_tiles: partial sum of the tile's first row when it began in an earlier tile
+    // algorithmic bytes of one y = A x with this matrix: 12*Z + 4*(R+1) + 8*C + 8*R
+    u64 spmv_bytes() const { return 12 * nnz + 4 * (rows + 1) + 8 * cols + 8 * rows; }
+};
+
+struct HostSparse {
+    int fmt; // SVDLAS2_FMT_*
+    u64 nrows, ncols, nnz;
+    const u64 *a; // CSR/CSC: major offsets; COO: row indices
+    const u64 *b; // CSR/CSC: minor indices; COO: col indices
+    const double *val;
+};
+
+struct UploadStats {
+    u64 h2d_bytes = 0;
+    u64 launches = 0;
+};
+
+// Builds CSR(B) and CSR(B') on the current device.  `transposed` is the orientation decision of
+// src/lib.rs:606 (B = A' when true).  Throws Error(SVDLAS2_ERR_INVALID_ARGUMENT) on malformed input.
+void build_operator(const HostSparse &A, bool transposed, cudaStream_t stream, DeviceCsr &B, DeviceCsr &BT,
+                    UploadStats &stats);
+
+// Builds the pair from a CSR row shard that is already oriented (multi-GPU path).
+void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, const u64 *indices,
+                             const double *values, cudaStream_t stream, DeviceCsr &B, DeviceCsr &BT,
+                             UploadStats &stats);
+
+} // namespace las2

@@ -1,0 +1,519 @@
+// las2.cu -- the LAS2 driver: host control flow of lanso / lanczos_step / purge / ritvec, every O(N) or
+// O(nnz) operation a kernel launch on the operator's stream.
+//
+// Reference call tree (src/lib.rs): svdLAS2 :570-655 -> lanso :1925-2017 -> stpone :1179-1201 / startv
+// :1098-1147 -> lanczos_step :1233-1319 -> ortbnd :1431-1453, purge :1356-1400 -> imtqlb :962-1068,
+// error_bound :1480-1532 -> ritvec :1767-1879 -> imtql2 :1576-1693.
+//
+// Device-resident state (replaces WorkSpace :740-779 and Store :707-737):
+//   Q      N x J column-major panel of Lanczos vectors, leading dimension ld = roundup(N, 32).  Column j IS
+//          the reference's w1 at step j (q_j); w2 is column j-1.  The reference's p-vectors (w3, w4 and
+//          storp) are bitwise copies of the q-vectors at every point they are read (datx and dscal compute the
+//          same products, :903-914), so they need no storage here.
+//   r      the residual (w0; w4 is its copy taken right before every norm)
+//   t      M-vector between the two SpMVs of opb (temp)
+// Scalars (alf, bet, rnm, reorthogonalisation coefficients) are produced as per-CTA partials, consumed on the
+// device by the next kernel of the chain, and read back ONCE per Lanczos step (one extra time per purge pass)
+// for the host-side recurrences (ortbnd, the purge trigger, tol).
+#include "las2.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "spmv.cuh"
+#include "tridiag_device.cuh"
+
+namespace las2 {
+
+// vecops.cu
+void vec_sigma_scale(double *u, u64 m, const PartialSlot &t, double *sigma_out, cudaStream_t s);
+
+namespace {
+
+constexpr u64 kMaxLL = 2; // MAXLL, src/lib.rs:665
+
+double wall() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
+
+struct Solver {
+    Operator &op;
+    cudaStream_t s;
+    const u64 N, M, ld;
+    const u64 dims, iters;
+    const double eps1; // eps * sqrt(N): roundoff estimate for the dot product of two unit vectors
+
+    // device
+    DevBuf<double> Q;
+    u64 qcap = 0, qused = 0;
+    DevBuf<double> r, xs, t;
+    DevBuf<double> parts;
+    PartialSlot slot[8];
+    PinnedBuf<double> hs;
+    PanelWork pw;
+    // host (WorkSpace arrays, src/lib.rs:770-775)
+    std::vector<double> alf, bet, eta, oldeta, ritz, bnd, w5;
+    svdlas2_profile prof;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> opb_events;
+
+    Solver(Operator &o, u64 dimensions, u64 iterations)
+        : op(o), s(o.stream), N(o.N), M(o.M), ld(round_up(o.N, 32)), dims(dimensions), iters(iterations),
+          eps1(kEps * std::sqrt((double)o.N)) {
+        std::memset(&prof, 0, sizeof prof);
+        r.alloc(ld); xs.alloc(ld); t.alloc(M ? M : 1);
+        LAS2_CUDA(cudaMemsetAsync(r.get(), 0, ld * sizeof(double), s));
+        LAS2_CUDA(cudaMemsetAsync(xs.get(), 0, ld * sizeof(double), s));
+        parts.alloc(8 * (size_t)kMaxParts);
+        for (int i = 0; i < 8; i++) slot[i] = PartialSlot{parts.get() + (size_t)i * kMaxParts, 0};
+        hs.alloc(16);
+        alf.assign(iters, 0.0); eta.assign(iters, 0.0); oldeta.assign(iters, 0.0);
+        bet.assign(iters + 1, 0.0); ritz.assign(iters + 1, 0.0);
+        bnd.assign(iters + 1, 1.7976931348623157e308); // f64::MAX, :775
+        w5.assign(iters + 2, 0.0);
+    }
+    ~Solver() {
+        for (auto &e : opb_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    }
+
+    double *q(u64 j) { return Q.get() + j * ld; }
+
+    void ensure_cols(u64 need) {
+        if (need <= qcap) return;
+        u64 cap = qcap ? qcap * 2 : std::max<u64>(64, 2 * (std::max<u64>(dims, 8) + dims));
+        if (cap < need) cap = need;
+        if (cap > iters + 1) cap = std::max(need, iters + 1);
+        DevBuf<double> nq(cap * ld);
+        if (qused) LAS2_CUDA(cudaMemcpyAsync(nq.get(), Q.get(), qused * ld * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        Q = std::move(nq);
+        qcap = cap;
+    }
+
+    void opb(const double *x, double *y) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (op.profile) {
+            LAS2_CUDA(cudaEventCreate(&e0)); LAS2_CUDA(cudaEventCreate(&e1));
+            LAS2_CUDA(cudaEventRecord(e0, s));
+        }
+        op.opb(x, y, t.get(), &prof.n_kernel_launches);
+        if (op.profile) {
+            LAS2_CUDA(cudaEventRecord(e1, s));
+            opb_events.emplace_back(e0, e1);
+        }
+        prof.n_opb += 1;
+        prof.n_spmv += 2;
+    }
+
+    // read back the canonical sums of the given partial slots (one sync)
+    void gather(std::initializer_list<int> which, double *out) {
+        GatherList g;
+        g.count = 0;
+        for (int w : which) { g.parts[g.count] = slot[w].parts; g.nparts[g.count] = slot[w].nparts; g.count++; }
+        gather_scalars(g, hs.get(), s);
+        prof.n_kernel_launches += 1;
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        prof.n_host_syncs += 1;
+        for (int i = 0; i < g.count; i++) out[i] = hs[i];
+    }
+
+    Coef sum_of(int w) const { return Coef::partials(slot[w].parts, slot[w].nparts); }
+
+    // ---- startv (src/lib.rs:1098-1147): r <- B'B(random); on a restart also swept against q_0..q_{step-1} ----
+    double startv(u64 step, uint32_t seed) {
+        {
+            std::vector<double> h(ld, 0.0);
+            ChaCha12Stream g(seed); // rebuilt from the same seed on every call, :1109-1114
+            for (u64 i = 0; i < N; i++) h[i] = g.next_unit_pm1();
+            LAS2_CUDA(cudaMemcpyAsync(xs.get(), h.data(), ld * sizeof(double), cudaMemcpyHostToDevice, s));
+            LAS2_CUDA(cudaStreamSynchronize(s));
+            prof.h2d_bytes += ld * sizeof(double);
+        }
+        opb(xs.get(), r.get()); // apply the operator to put r in range (essential if B singular)
+        vec_dot(r.get(), r.get(), ld, slot[0], s);
+        prof.n_kernel_launches += 1;
+        double rnm2;
+        gather({0}, &rnm2);
+        // the reference retries up to three times with the SAME regenerated vector, so one try decides
+        if (!(rnm2 > 0.0)) throw Error(SVDLAS2_ERR_STARTV, "rnm2 <= 0.0, rnm2 = " + std::to_string(rnm2));
+        if (step > 0) {
+            // w0 -= (w3 . q_i) q_i with w3 the frozen copy: classical GS against all stored vectors, :1132-1135
+            panel_cgs2(Q.get(), ld, N, 0, (u32)step, r.get(), nullptr, pw, &slot[1], &slot[2], nullptr, s,
+                       &prof.n_kernel_launches);
+            // make sure q[step] is orthogonal to q[step-1], :1138
+            vec_dot(q(step - 1), r.get(), ld, slot[3], s);
+            vec_axpy_dot(r.get(), q(step - 1), sum_of(3), nullptr, ld, slot[4], s);
+            prof.n_kernel_launches += 2;
+            double dot;
+            gather({4}, &dot);
+            rnm2 = (dot <= kEps * rnm2) ? 0.0 : dot;
+        }
+        return std::sqrt(rnm2);
+    }
+
+    // ---- stpone (src/lib.rs:1179-1201) ----
+    void stpone(uint32_t seed, double *rnm, double *tol) {
+        double n0 = startv(0, seed);
+        if (near(n0, 0.0)) throw Error(SVDLAS2_ERR_STPONE, "rnm == 0.0");
+        ensure_cols(1);
+        vec_scale(q(0), r.get(), 1.0 / n0, ld, s); // normalize starting vector
+        qused = 1;
+        opb(q(0), r.get());                         // take the first step
+        vec_dot(r.get(), q(0), ld, slot[0], s);
+        vec_axpy_dot(r.get(), q(0), sum_of(0), q(0), ld, slot[1], s);
+        vec_axpy_dot(r.get(), q(0), sum_of(1), nullptr, ld, slot[2], s);
+        prof.n_kernel_launches += 4;
+        double v[3];
+        gather({0, 1, 2}, v);
+        alf[0] = v[0];
+        alf[0] += v[1];
+        *rnm = std::sqrt(v[2]);
+        const double anorm = *rnm + std::fabs(alf[0]);
+        *tol = std::sqrt(kEps) * anorm;
+    }
+
+    // ---- ortbnd (src/lib.rs:1431-1453): the eta recurrence, host O(j) ----
+    void ortbnd(u64 step, double rnm) {
+        if (step < 1) return;
+        if (!near(rnm, 0.0) && step > 1) {
+            oldeta[0] = (bet[1] * eta[1] + (alf[0] - alf[step]) * eta[0] - bet[step] * oldeta[0]) / rnm + eps1;
+            for (u64 i = 1; i + 2 <= step; i++)
+                oldeta[i] = (bet[i + 1] * eta[i + 1] + (alf[i] - alf[step]) * eta[i] + bet[i] * eta[i - 1] -
+                             bet[step] * oldeta[i]) / rnm + eps1;
+        }
+        oldeta[step - 1] = eps1;
+        eta.swap(oldeta);
+        eta[step] = eps1;
+    }
+
+    // ---- purge (src/lib.rs:1356-1400): reorthogonalise r and q_step against q_ll..q_{step-1} when eta says so ----
+    void purge(u64 ll, u64 step, double *rnm, double tol) {
+        if (step < ll + 2) return;
+        const double reps = std::sqrt(kEps);
+        // NB the scan starts at eta[0] and ll is added afterwards (reference behaviour, :1364)
+        const u64 k = argmax_abs(step - (ll + 1), eta.data()) + ll;
+        if (!(std::fabs(eta[k]) > reps)) return;
+        prof.n_purge_fired += 1;
+        const double reps1 = eps1 / reps;
+        bool again = true;
+        for (int pass = 0; pass < 2 && again; pass++) {
+            if (*rnm > tol) {
+                // c = Q'[q r] against the frozen pair, [q r] -= Q c, then t = r . q (new), :1374-1384
+                panel_cgs2(Q.get(), ld, N, (u32)ll, (u32)(step - ll), q(step), r.get(), pw, &slot[0], &slot[1],
+                           &slot[2], s, &prof.n_kernel_launches);
+                vec_axpy_dot(r.get(), q(step), sum_of(2), nullptr, ld, slot[3], s); // r -= t q ; |r|^2, :1386-1388
+                prof.n_kernel_launches += 1;
+                double v[4];
+                gather({0, 1, 2, 3}, v);
+                const double tq = v[0];
+                const double tr = v[1] + std::fabs(v[2]);
+                *rnm = std::sqrt(v[3]);
+                prof.n_purge_passes += 1;
+                prof.n_purge_vectors += step - ll;
+                if (tq <= reps1 && tr <= *rnm * reps1) again = false;
+            }
+        }
+        for (u64 i = ll; i <= step; i++) { eta[i] = eps1; oldeta[i] = eps1; }
+    }
+
+    // ---- lanczos_step (src/lib.rs:1233-1319) ----
+    u64 lanczos_step(u64 first, u64 last, u64 *ll, bool *enough, double *rnm, double *tol) {
+        u64 j = first;
+        while (j < last) {
+            // (the reference's swaps / storq / storp are implicit: q_{j-1} already sits in panel column j-1)
+            bet[j] = *rnm;
+            // restart if invariant subspace is found
+            if (near(*rnm, 0.0)) {
+                prof.n_restarts += 1;
+                *rnm = startv(j, 0); // restarts always use seed 0, :1259
+                if (near(*rnm, 0.0)) *enough = true;
+            }
+            if (*enough) break;
+
+            // take a lanczos step
+            ensure_cols(j + 1);
+            const double rn = *rnm;
+            vec_scale(q(j), r.get(), 1.0 / rn, ld, s);
+            qused = j + 1;
+            opb(q(j), r.get());
+            int ns = 0; // slots in use for this step
+            vec_axpy_dot(r.get(), q(j - 1), Coef::value(rn), q(j), ld, slot[ns], s); // r -= rnm q_{j-1} ; alf = r.q_j
+            prof.n_kernel_launches += 2;
+            const int s_alf = ns++;
+            if (j <= kMaxLL) {
+                // |alf[j-1]| > 4 |alf[j]| decides ll only while j <= MAXLL (:1282): needs alf[j] now
+                double a;
+                gather({s_alf}, &a);
+                if (std::fabs(alf[j - 1]) > 4.0 * std::fabs(a)) *ll = j;
+            }
+            // r -= alf q_j, then orthogonalize against the first ll Lanczos vectors (:1285-1292) ...
+            const double *ax = q(j);
+            int prev = s_alf;
+            const u64 lim = std::min<u64>(j - 1, *ll);
+            int s_ll[2] = {-1, -1};
+            for (u64 i = 0; i < lim; i++) {
+                vec_axpy_dot(r.get(), ax, sum_of(prev), q(i), ld, slot[ns], s);
+                prof.n_kernel_launches += 1;
+                ax = q(i);
+                prev = ns;
+                s_ll[i] = ns++;
+                eta[i] = eps1;
+                oldeta[i] = eps1;
+            }
+            // ... and the extended local reorthogonalization (:1295-1304)
+            vec_axpy_dot(r.get(), ax, sum_of(prev), q(j - 1), ld, slot[ns], s); // t1 = r . q_{j-1}
+            const int s_t1 = ns++;
+            vec_axpy_dot(r.get(), q(j - 1), sum_of(s_t1), q(j), ld, slot[ns], s); // r -= t1 q_{j-1} ; t2 = r . q_j
+            const int s_t2 = ns++;
+            vec_axpy_dot(r.get(), q(j), sum_of(s_t2), nullptr, ld, slot[ns], s); // r -= t2 q_j ; |r|^2
+            const int s_nrm = ns++;
+            prof.n_kernel_launches += 3;
+            (void)s_ll;
+            double v[4];
+            gather({s_alf, s_t1, s_t2, s_nrm}, v); // the one read-back of this step
+            const double nrm2 = v[3];
+            alf[j] = v[0];
+            if (bet[j] > 0.0) bet[j] += v[1];
+            alf[j] += v[2];
+            *rnm = std::sqrt(nrm2);
+            const double anorm = bet[j] + std::fabs(alf[j]) + *rnm;
+            *tol = std::sqrt(kEps) * anorm;
+
+            ortbnd(j, *rnm);                 // update the orthogonality bounds
+            purge(*ll, j, rnm, *tol);        // restore the orthogonality state when needed
+            if (*rnm <= *tol) *rnm = 0.0;
+            j += 1;
+        }
+        return j;
+    }
+
+    // ---- lanso (src/lib.rs:1925-2017) ----
+    u64 lanso(const double end_interval[2], uint32_t seed, u64 *neig_out) {
+        const double endl = end_interval[0], endr = end_interval[1];
+        double rnm, tol;
+        stpone(seed, &rnm, &tol);
+        eta[0] = eps1;
+        oldeta[0] = eps1;
+        u64 ll = 0, first = 1;
+        u64 last = std::min(iters, std::max<u64>(dims, 8) + dims);
+        bool enough = false;
+        u64 j = 0, intro = 0, neig = 0;
+
+        while (!enough) {
+            if (rnm <= tol) rnm = 0.0;
+            const u64 steps = lanczos_step(first, last, &ll, &enough, &rnm, &tol);
+            j = enough ? steps - 1 : last - 1;
+            first = j + 1;
+            bet[first] = rnm;
+
+            // analyze T: eigenvalues + last-row eigenvector components of every unreduced block
+            u64 l = 0;
+            for (u64 id2 = 0; id2 < j; id2++) {
+                if (l > j) break;
+                u64 i = l;
+                while (i <= j && !near(bet[i + 1], 0.0)) i++;
+                i = std::min(i, j);
+                const u64 sz = i - l;
+                for (u64 k = 0; k <= sz; k++) ritz[l + sz - k] = alf[l + k];     // svd_dcopy reverses, :1985
+                for (u64 k = 0; k < sz; k++) w5[l + 1 + (sz - 1) - k] = bet[l + 1 + k]; // :1986
+                int rc = ql_values(sz + 1, &ritz[l], &w5[l], &bnd[l]);
+                if (rc == SVDLAS2_ERR_IMTQLB)
+                    throw Error(rc, "imtqlb no convergence to an eigenvalue after 30 iterations");
+                if (rc) throw Error(rc, "imtqlb: expected 'm' to be non-zero");
+                for (u64 m = l; m <= i; m++) bnd[m] = rnm * std::fabs(bnd[m]);
+                l = i + 1;
+            }
+            cosort_ascending(j + 1, ritz.data(), bnd.data());
+            size_t ne = 0;
+            int rc = refine_bounds(&enough, endl, endr, ritz.data(), bnd.data(), j, tol, &ne);
+            if (rc) throw Error(rc, "error_bound: expected 'step' to be non-zero");
+            neig = ne;
+
+            // should we stop?
+            if (neig < dims) {
+                if (neig == 0) {
+                    last = first + 9;
+                    intro = first;
+                } else {
+                    last = first + std::max<u64>(3, 1 + ((j - intro) * (dims - neig)) / neig);
+                }
+                last = std::min(last, iters);
+            } else {
+                enough = true;
+            }
+            enough = enough || first >= iters;
+        }
+        *neig_out = neig;
+        return j;
+    }
+
+    // ---- ritvec (src/lib.rs:1767-1879) ----
+    void ritvec(u64 steps, u64 neig, double kappa, svdlas2_result *res, double *t_imtql2) {
+        const u64 js = steps + 1;
+        std::vector<double> dd(js), ee(js + 1, 0.0);
+        for (u64 i = 0; i < js; i++) dd[js - 1 - i] = alf[i];                   // svd_dcopy(js, 0, alf, ..), :1790
+        for (u64 i = 0; i < steps; i++) ee[1 + (steps - 1) - i] = bet[1 + i];  // svd_dcopy(steps, 1, bet, w5), :1791
+
+        const double tq0 = wall();
+        QlPlan plan;
+        int rc = ql_rotations(js, dd.data(), ee.data(), plan);
+        if (rc == SVDLAS2_ERR_IMTQL2) throw Error(rc, "imtql2 no convergence to an eigenvalue after 30 iterations");
+        if (rc) throw Error(rc, "imtql2: expected 'm' to be non-zero");
+        const u32 ldz = (u32)round_up(js, 32);
+        DevBuf<double> zT((size_t)ldz * js);
+        ql_replay(plan, (u32)js, ldz, zT.get(), s, &prof.n_kernel_launches, &prof.h2d_bytes);
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        *t_imtql2 = wall() - tq0;
+
+        // acceptance (:1800-1801) in ascending eigenvalue order; the reference's circular buffer + rotate_array
+        // keep the LAST `dims` accepted, largest first (:1802-1827)
+        std::vector<u64> accepted;
+        for (u64 k = 0; k < js; k++)
+            if (bnd[k] <= kappa * std::fabs(ritz[k]) && k + 1 > js - neig) accepted.push_back(k);
+        const u64 nsig = accepted.size();
+        const u64 d = std::min(dims, nsig);
+        res->d = d;
+        res->diagnostics.significant_values = d;   // sic, :648
+        res->diagnostics.singular_values = nsig;   // sic, :649
+
+        const u64 mcols = M, ncols = N;
+        double *hV = (double *)std::malloc(std::max<size_t>(1, d * ncols) * sizeof(double));
+        double *hU = (double *)std::malloc(std::max<size_t>(1, d * mcols) * sizeof(double));
+        double *hS = (double *)std::malloc(std::max<size_t>(1, d) * sizeof(double));
+        if (!hV || !hU || !hS) { std::free(hV); std::free(hU); std::free(hS); throw Error(SVDLAS2_ERR_ALLOC, "host result allocation failed"); }
+        // hand ownership to the result right away so that an exception below cannot leak
+        const bool tr = op.transposed;
+        res->ut = tr ? hV : hU; res->ut_cols = tr ? ncols : mcols;
+        res->vt = tr ? hU : hV; res->vt_cols = tr ? mcols : ncols;
+        res->s = hS;
+        if (d == 0) return;
+
+        std::vector<u32> phys(d);
+        for (u64 i = 0; i < d; i++) phys[i] = plan.column_of[accepted[nsig - 1 - i]];
+        DevBuf<u32> dphys(d);
+        LAS2_CUDA(cudaMemcpyAsync(dphys.get(), phys.data(), d * sizeof(u32), cudaMemcpyHostToDevice, s));
+        DevBuf<double> C((size_t)js * d);
+        ritz_coefficients(zT.get(), ldz, (u32)js, dphys.get(), (u32)d, C.get(), s, &prof.n_kernel_launches);
+        DevBuf<double> V((size_t)d * ld);
+        ritz_contract(Q.get(), ld, N, (u32)js, C.get(), (u32)d, V.get(), s, &prof.n_kernel_launches);
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        zT.release();
+        C.release();
+        Q.release(); // the panel is no longer needed; make room for U
+        qcap = qused = 0;
+
+        // sigma_i = sqrt(v_i . B'B v_i), u_i = B v_i / sigma_i (:1839-1859).  B v_i is computed once and reused.
+        DevBuf<double> U((size_t)d * mcols);
+        DevBuf<double> S(d);
+        for (u64 i = 0; i < d; i++) {
+            double *vi = V.get() + i * ld;
+            double *ui = U.get() + i * mcols;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (op.profile) { LAS2_CUDA(cudaEventCreate(&e0)); LAS2_CUDA(cudaEventCreate(&e1)); LAS2_CUDA(cudaEventRecord(e0, s)); }
+            spmv(op.B, vi, ui, s, &prof.n_kernel_launches);
+            spmv(op.BT, ui, r.get(), s, &prof.n_kernel_launches);
+            if (op.comm) op.comm->allreduce_sum(r.get(), N, s);
+            if (op.profile) { LAS2_CUDA(cudaEventRecord(e1, s)); opb_events.emplace_back(e0, e1); }
+            prof.n_opb += 1;
+            prof.n_spmv += 2;
+            vec_dot(vi, r.get(), ld, slot[0], s);
+            vec_sigma_scale(ui, mcols, slot[0], S.get() + i, s);
+            prof.n_kernel_launches += 2;
+        }
+        const double td0 = wall();
+        LAS2_CUDA(cudaMemcpy2DAsync(hV, ncols * sizeof(double), V.get(), ld * sizeof(double), ncols * sizeof(double), d,
+                                    cudaMemcpyDeviceToHost, s));
+        LAS2_CUDA(cudaMemcpyAsync(hU, U.get(), d * mcols * sizeof(double), cudaMemcpyDeviceToHost, s));
+        LAS2_CUDA(cudaMemcpyAsync(hS, S.get(), d * sizeof(double), cudaMemcpyDeviceToHost, s));
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        prof.n_host_syncs += 1;
+        prof.d2h_bytes += (d * ncols + d * mcols + d) * sizeof(double);
+        prof.t_download = wall() - td0; // includes waiting for the tail kernels queued before the copies
+    }
+};
+
+} // namespace
+
+Operator::~Operator() {
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Operator::opb(const double *x, double *y, double *t, u64 *launches) {
+    spmv(B, x, t, stream, launches);
+    spmv(BT, t, y, stream, launches);
+    if (comm) comm->allreduce_sum(y, N, stream);
+}
+
+void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interval[2], double kappa,
+           uint32_t random_seed, svdlas2_result *res) {
+    const double t0 = wall();
+    LAS2_CUDA(cudaSetDevice(op.device));
+    if (!(random_seed > 0)) random_seed = entropy_seed_u32(); // :578-581
+
+    // clamping uses the un-oriented shape (:583-594)
+    const u64 mn = std::min(op.a_rows, op.a_cols);
+    if (dimensions == 0 || dimensions > mn) dimensions = mn;
+    if (iterations == 0 || iterations > mn) iterations = mn;
+    else if (iterations < dimensions) iterations = dimensions;
+
+    svdlas2_diagnostics &dg = res->diagnostics;
+    dg.non_zero = op.nnz_global;
+    dg.dimensions = dimensions;
+    dg.iterations = iterations;
+    dg.transposed = op.transposed ? 1 : 0;
+    dg.end_interval[0] = end_interval[0];
+    dg.end_interval[1] = end_interval[1];
+    dg.random_seed = random_seed;
+    dg.kappa = kappa;
+    if (dimensions < 2)
+        throw Error(SVDLAS2_ERR_LAS2, "svdLAS2: insufficient dimensions: " + std::to_string(dimensions)); // :596-600
+
+    Solver sv(op, dimensions, iterations);
+    u64 neig = 0;
+    const double tl0 = wall();
+    const u64 steps = sv.lanso(end_interval, random_seed, &neig);
+    sv.prof.t_lanczos = wall() - tl0;
+
+    kappa = std::max(std::fabs(kappa), eps34()); // :627
+    dg.kappa = kappa;
+    dg.lanczos_steps = steps + 1;
+    dg.ritz_values_stabilized = neig;
+
+    // trace for step-by-step parity tests
+    const u64 js = steps + 1;
+    res->trace_len = js;
+    res->alf = (double *)std::malloc(js * sizeof(double));
+    res->bet = (double *)std::malloc((js + 1) * sizeof(double));
+    res->ritz = (double *)std::malloc(js * sizeof(double));
+    res->bnd = (double *)std::malloc(js * sizeof(double));
+    if (!res->alf || !res->bet || !res->ritz || !res->bnd) throw Error(SVDLAS2_ERR_ALLOC, "host trace allocation failed");
+    std::memcpy(res->alf, sv.alf.data(), js * sizeof(double));
+    std::memcpy(res->bet, sv.bet.data(), (js + 1) * sizeof(double));
+    std::memcpy(res->ritz, sv.ritz.data(), js * sizeof(double));
+    std::memcpy(res->bnd, sv.bnd.data(), js * sizeof(double));
+
+    const double tr0 = wall();
+    double t_imtql2 = 0.0;
+    sv.ritvec(steps, neig, kappa, res, &t_imtql2);
+    sv.prof.t_ritvec = wall() - tr0;
+    sv.prof.t_imtql2 = t_imtql2;
+
+    if (op.profile) {
+        double ms_total = 0.0;
+        for (auto &e : sv.opb_events) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) ms_total += ms;
+        }
+        sv.prof.t_opb_device = ms_total * 1e-3;
+    }
+    sv.prof.t_upload = op.t_upload;
+    sv.prof.h2d_bytes += op.upload.h2d_bytes;
+    sv.prof.opb_algorithmic_bytes = op.opb_bytes();
+    sv.prof.t_total = wall() - t0;
+    res->profile = sv.prof;
+}
+
+} // namespace las2

@@ -1,0 +1,49 @@
+// las2.hpp -- the resident operator and the LAS2 driver (host control + kernel launches).
+#pragma once
+
+#include <memory>
+#include <vector>
+
+#include "comm.hpp"
+#include "device_csr.cuh"
+#include "host_math.hpp"
+#include "vecops.cuh"
+
+namespace las2 {
+
+// The operator B (M x N, M >= N "mostly": B = A, or A' when cols(A) >= 1.2 rows(A), src/lib.rs:606-608),
+// resident in HBM as CSR(B) + CSR(B').  In a multi-GPU run each rank holds a contiguous row range of B.
+struct Operator {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // shape of the caller's matrix A and of the oriented operator
+    u64 a_rows = 0, a_cols = 0, nnz_global = 0;
+    bool transposed = false;
+    u64 M_global = 0; // rows of B over all ranks
+    u64 M = 0;        // rows of B held here
+    u64 N = 0;
+    u64 row_begin = 0;
+    DeviceCsr B, BT; // BT is N x M (local)
+    std::unique_ptr<Comm> comm; // null on a single GPU
+    // scratch for opa/opb/time_opb
+    DevBuf<double> tmp_m, tmp_x, tmp_y;
+    DevBuf<char> l2_flush;
+    // knobs
+    bool profile = false;
+    // bookkeeping
+    UploadStats upload;
+    double t_upload = 0.0;
+
+    ~Operator();
+    u64 opb_bytes() const { return B.spmv_bytes() + BT.spmv_bytes(); } // 24 Z + 20 (M + N) + 8
+    // y = B'(B x) on the stream; x, y device N-vectors (y != x); t scratch of M doubles
+    void opb(const double *x, double *y, double *t, u64 *launches);
+};
+
+struct SolveOutput; // svdlas2_result with owned buffers (abi.cu)
+
+// svdLAS2 (src/lib.rs:570-655) on a resident operator; fills *res (already calloc'ed). Throws las2::Error.
+void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interval[2], double kappa,
+           uint32_t random_seed, svdlas2_result *res);
+
+} // namespace las2

@@ -1,0 +1,267 @@
+// panel.cu -- blocked operations on the device-resident Lanczos-vector panel Q (N x J, column-major).
+//
+//  * panel_cgs2: the reorthogonalisation sweep of purge (reference src/lib.rs:1372-1388) and of the restart
+//    path of startv (:1132-1135) as a tall-skinny GEMV pair  c = Q'[a b]  then  [a b] -= Q c.
+//    The reference computes every coefficient against FROZEN copies (w3, w4) while it updates (w1, w0), i.e.
+//    classical Gram-Schmidt, so "all dots first, then all updates" is the same arithmetic; the update keeps
+//    the reference's order (k ascending, one rounded multiply and one rounded add per term).
+//    Minimum traffic: 2 * ncols * N * 8 B (Q is read twice) + 6 * N * 8 B -- HBM-bound.
+//  * ritz_contract: the Ritz back-transform V = Q Z_sel of ritvec (:1807-1817) on the FP64 FMA pipe.
+#include "vecops.cuh"
+
+namespace las2 {
+
+namespace {
+
+constexpr int kPanelRows = 2048; // rows of (a, b) staged in shared memory per CTA
+constexpr int kPanelThreads = 256;
+constexpr int kPanelWarps = kPanelThreads / 32;
+
+// partials[(rb * ncols + c) * NRHS + rhs] = sum over the row block rb of Q[i, col0 + c] * rhs[i]
+template <int NRHS>
+__global__ void __launch_bounds__(kPanelThreads)
+k_panel_dots(const double *__restrict__ Q, u64 ld, u32 col0, u32 ncols, const double *__restrict__ a,
+             const double *__restrict__ b, double *__restrict__ partials) {
+    __shared__ __align__(16) double sa[kPanelRows];
+    __shared__ __align__(16) double sb[NRHS > 1 ? kPanelRows : 2];
+    const u64 row0 = (u64)blockIdx.x * kPanelRows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kPanelRows; i += kPanelThreads) {
+        const u64 r = row0 + i;
+        sa[i] = (r < ld) ? a[r] : 0.0;
+        if (NRHS > 1) sb[i] = (r < ld) ? b[r] : 0.0;
+    }
+    __syncthreads();
+    const u32 rows_here = (u32)min((u64)kPanelRows, ld - row0); // multiple of 32 (ld is)
+    const u32 wslots = gridDim.y * kPanelWarps;
+    for (u32 c = blockIdx.y * kPanelWarps + warp; c < ncols; c += wslots) {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(Q + (u64)(col0 + c) * ld + row0);
+        double acc_a = 0.0, acc_b = 0.0;
+#pragma unroll 8
+        for (u32 i = lane; i < rows_here / 2; i += 32) {
+            const double2 qv = q[i];
+            const double2 av = *reinterpret_cast<const double2 *>(&sa[2 * i]);
+            acc_a = fma(qv.x, av.x, acc_a);
+            acc_a = fma(qv.y, av.y, acc_a);
+            if (NRHS > 1) {
+                const double2 bv = *reinterpret_cast<const double2 *>(&sb[2 * i]);
+                acc_b = fma(qv.x, bv.x, acc_b);
+                acc_b = fma(qv.y, bv.y, acc_b);
+            }
+        }
+        acc_a = warp_sum(acc_a);
+        if (NRHS > 1) acc_b = warp_sum(acc_b);
+        if (lane == 0) {
+            double *o = partials + ((u64)blockIdx.x * ncols + c) * NRHS;
+            o[0] = acc_a;
+            if (NRHS > 1) o[1] = acc_b;
+        }
+    }
+}
+
+// coeffs[rhs * ncols + c] = sum over row blocks (in order) ; abs_parts[blockIdx.x * 2 + rhs] = sum |coeff| of the CTA's columns
+template <int NRHS>
+__global__ void __launch_bounds__(128)
+k_panel_reduce(const double *__restrict__ partials, u32 nblocks, u32 ncols, double *__restrict__ coeffs,
+               double *__restrict__ abs_a, double *__restrict__ abs_b) {
+    __shared__ double sm[2][4];
+    const u32 c = blockIdx.x * 128 + threadIdx.x;
+    double ca = 0.0, cb = 0.0;
+    if (c < ncols) {
+        for (u32 rb = 0; rb < nblocks; rb++) {
+            const double *p = partials + ((u64)rb * ncols + c) * NRHS;
+            ca += p[0];
+            if (NRHS > 1) cb += p[1];
+        }
+        coeffs[c] = ca;
+        if (NRHS > 1) coeffs[ncols + c] = cb;
+    }
+    double va = warp_sum(fabs(ca)), vb = warp_sum(fabs(cb));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sm[0][warp] = va; sm[1][warp] = vb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        abs_a[blockIdx.x] = ((sm[0][0] + sm[0][1]) + sm[0][2]) + sm[0][3];
+        abs_b[blockIdx.x] = ((sm[1][0] + sm[1][1]) + sm[1][2]) + sm[1][3];
+    }
+}
+
+constexpr int kUpdThreads = 128;
+constexpr int kUpdChunk = 512; // coefficients staged per pass
+
+// a -= Q ca ; b -= Q cb (k ascending, mul then add, as the reference's chain of daxpys) ; partial of a . b
+template <int NRHS>
+__global__ void __launch_bounds__(kUpdThreads)
+k_panel_update(const double *__restrict__ Q, u64 ld, u32 col0, u32 ncols, const double *__restrict__ coeffs,
+               double *__restrict__ a, double *__restrict__ b, double *__restrict__ dot_parts) {
+    __shared__ double sc[NRHS][kUpdChunk];
+    __shared__ double sm[kUpdThreads / 32];
+    const u64 i = (u64)blockIdx.x * kUpdThreads + threadIdx.x; // double2 index
+    const bool live = i < ld / 2;
+    double2 av = make_double2(0.0, 0.0), bv = make_double2(0.0, 0.0);
+    if (live) {
+        av = reinterpret_cast<double2 *>(a)[i];
+        if (NRHS > 1) bv = reinterpret_cast<double2 *>(b)[i];
+    }
+    for (u32 c0 = 0; c0 < ncols; c0 += kUpdChunk) {
+        const u32 nc = min((u32)kUpdChunk, ncols - c0);
+        __syncthreads();
+        for (u32 k = threadIdx.x; k < nc; k += kUpdThreads) {
+            sc[0][k] = -coeffs[c0 + k];
+            if (NRHS > 1) sc[1][k] = -coeffs[ncols + c0 + k];
+        }
+        __syncthreads();
+        if (live) {
+            const double2 *__restrict__ q = reinterpret_cast<const double2 *>(Q + (u64)(col0 + c0) * ld) + i;
+            const u64 ld2 = ld / 2;
+#pragma unroll 8
+            for (u32 k = 0; k < nc; k++) {
+                const double2 qv = q[(u64)k * ld2];
+                av.x = __dadd_rn(av.x, __dmul_rn(sc[0][k], qv.x));
+                av.y = __dadd_rn(av.y, __dmul_rn(sc[0][k], qv.y));
+                if (NRHS > 1) {
+                    bv.x = __dadd_rn(bv.x, __dmul_rn(sc[1][k], qv.x));
+                    bv.y = __dadd_rn(bv.y, __dmul_rn(sc[1][k], qv.y));
+                }
+            }
+        }
+    }
+    double acc = 0.0;
+    if (live) {
+        reinterpret_cast<double2 *>(a)[i] = av;
+        if (NRHS > 1) {
+            reinterpret_cast<double2 *>(b)[i] = bv;
+            acc = fma(av.x, bv.x, 0.0);
+            acc = fma(av.y, bv.y, acc);
+        }
+    }
+    if (NRHS > 1 && dot_parts) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        acc = warp_sum(acc);
+        if (lane == 0) sm[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) dot_parts[blockIdx.x] = ((sm[0] + sm[1]) + sm[2]) + sm[3];
+    }
+}
+
+// second-stage for dot partials when the update grid exceeds kMaxParts: fold groups of partials in order
+__global__ void k_fold_partials(const double *__restrict__ in, u32 n, u32 group, double *__restrict__ out) {
+    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 lo = g * group;
+    if (lo >= n) return;
+    u32 hi = min(lo + group, n);
+    double s = 0.0;
+    for (u32 i = lo; i < hi; i++) s += in[i];
+    out[g] = s;
+}
+
+// ---- Ritz contraction ---------------------------------------------------------------------------------
+constexpr int kRitzThreads = 128;
+constexpr int kRitzCols = 8;   // output columns per thread (x2 rows = 16 accumulators)
+constexpr int kRitzChunk = 256;
+
+__global__ void __launch_bounds__(kRitzThreads)
+k_ritz_contract(const double *__restrict__ Q, u64 ld, u32 js, const double *__restrict__ C, u32 d,
+                double *__restrict__ V) {
+    __shared__ double sc[kRitzChunk][kRitzCols];
+    const u64 i = (u64)blockIdx.x * kRitzThreads + threadIdx.x; // double2 row index
+    const u32 c0 = blockIdx.y * kRitzCols;
+    const bool live = i < ld / 2;
+    double2 acc[kRitzCols];
+#pragma unroll
+    for (int t = 0; t < kRitzCols; t++) acc[t] = make_double2(0.0, 0.0);
+    const u64 ld2 = ld / 2;
+    for (u32 k0 = 0; k0 < js; k0 += kRitzChunk) {
+        const u32 nk = min((u32)kRitzChunk, js - k0);
+        __syncthreads();
+        for (u32 e = threadIdx.x; e < nk * kRitzCols; e += kRitzThreads) {
+            const u32 k = e / kRitzCols, t = e % kRitzCols;
+            sc[k][t] = (c0 + t < d) ? C[(u64)(k0 + k) * d + c0 + t] : 0.0;
+        }
+        __syncthreads();
+        if (live) {
+            const double2 *__restrict__ q = reinterpret_cast<const double2 *>(Q + (u64)k0 * ld) + i;
+#pragma unroll 4
+            for (u32 k = 0; k < nk; k++) {
+                const double2 qv = q[(u64)k * ld2];
+#pragma unroll
+                for (int t = 0; t < kRitzCols; t++) {
+                    acc[t].x = fma(sc[k][t], qv.x, acc[t].x);
+                    acc[t].y = fma(sc[k][t], qv.y, acc[t].y);
+                }
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int t = 0; t < kRitzCols; t++)
+            if (c0 + t < d) reinterpret_cast<double2 *>(V + (u64)(c0 + t) * ld)[i] = acc[t];
+    }
+}
+
+} // namespace
+
+void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, double *b, PanelWork &work,
+                PartialSlot *abs_a, PartialSlot *abs_b, PartialSlot *dot_out, cudaStream_t s, u64 *launches) {
+    (void)n;
+    if (ncols == 0) return;
+    const u32 nblocks = cdiv(ld, kPanelRows);
+    if (work.cap_cols < ncols || work.cap_blocks < nblocks) {
+        size_t cc = work.cap_cols < ncols ? (size_t)ncols * 2 : work.cap_cols;
+        work.partials.alloc((size_t)nblocks * cc * 2);
+        work.coeffs.alloc(cc * 2);
+        work.cap_cols = cc;
+        work.cap_blocks = nblocks;
+    }
+    u32 cs = cdiv(kMaxParts, nblocks);
+    const u32 max_cs = cdiv(ncols, kPanelWarps);
+    if (cs > max_cs) cs = max_cs;
+    if (cs < 1) cs = 1;
+    const u32 nred = cdiv(ncols, 128);
+    if (nred > (u32)kMaxParts) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "panel_cgs2: too many columns");
+    dim3 grid(nblocks, cs);
+    const u32 ugrid = cdiv(ld / 2, kUpdThreads);
+    if (b) {
+        k_panel_dots<2><<<grid, kPanelThreads, 0, s>>>(Q, ld, col0, ncols, a, b, work.partials);
+        k_panel_reduce<2><<<nred, 128, 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
+        abs_a->nparts = abs_b->nparts = (int)nred;
+        // dot partials: one per update CTA, folded to <= kMaxParts
+        double *dp = dot_out ? dot_out->parts : nullptr;
+        if (dot_out && ugrid > (u32)kMaxParts) {
+            if (work.dotparts.size() < ugrid) work.dotparts.alloc(ugrid);
+            dp = work.dotparts;
+        }
+        k_panel_update<2><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, b, dp);
+        if (launches) *launches += 3;
+        if (dot_out) {
+            if (ugrid > (u32)kMaxParts) {
+                const u32 group = cdiv(ugrid, kMaxParts);
+                const u32 ng = cdiv(ugrid, group);
+                k_fold_partials<<<cdiv(ng, 128), 128, 0, s>>>(dp, ugrid, group, dot_out->parts);
+                dot_out->nparts = (int)ng;
+                if (launches) *launches += 1;
+            } else {
+                dot_out->nparts = (int)ugrid;
+            }
+        }
+    } else {
+        k_panel_dots<1><<<grid, kPanelThreads, 0, s>>>(Q, ld, col0, ncols, a, nullptr, work.partials);
+        k_panel_reduce<1><<<nred, 128, 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
+        abs_a->nparts = abs_b->nparts = (int)nred;
+        k_panel_update<1><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, nullptr, nullptr);
+        if (launches) *launches += 3;
+    }
+    LAS2_LAUNCH_CHECK();
+}
+
+void ritz_contract(const double *Q, u64 ld, u64 n, u32 js, const double *C, u32 d, double *V, cudaStream_t s,
+                   u64 *launches) {
+    (void)n;
+    if (d == 0 || js == 0) return;
+    dim3 grid(cdiv(ld / 2, kRitzThreads), cdiv(d, kRitzCols));
+    k_ritz_contract<<<grid, kRitzThreads, 0, s>>>(Q, ld, js, C, d, V);
+    LAS2_LAUNCH_CHECK();
+    if (launches) *launches += 1;
+}
+
+} // namespace las2

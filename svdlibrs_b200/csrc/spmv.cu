@@ -1,0 +1,168 @@
+// spmv.cu -- y = A x for a device CSR matrix: the two halves of svd_opb (reference src/lib.rs:829-837,
+// gather forms :2051-2055 / :2087-2091; the scatter forms :2057-2061 / :2093-2097 never run on the device
+// because upload stores both B and B' in row-gather form).
+//
+// Kernel design ("nnz-tile stream"): the value / index arrays are cut into fixed tiles of kSpmvTile
+// non-zeros, one CTA per tile, independent of the row structure -- so the 12 B/nnz stream is read with
+// perfectly coalesced 128-bit / 64-bit loads even for power-law rows (length 1 .. 1e5+).  A tile
+//   1. streams its values and column indices (L1 no-allocate, L2 evict-first), gathers x (L1-cached, L2
+//      evict-last) and parks the products in shared memory;
+//   2. reduces the products per row: rows of <= 32 entries by one thread each, longer rows by one warp each
+//      (lanes stride, shuffle tree) -- both fixed-order, hence deterministic;
+//   3. writes y for rows that lie wholly inside the tile; the piece of a row that started in an earlier tile
+//      goes to head[tile], the piece of a row that continues into the next tile to carry[tile].
+// k_spmv_fixup then stitches the rows that straddle tiles (sum of carries in tile order + head).  No atomics.
+//
+// Algorithmic bytes per launch: 12*Z + 4*(R+1) + 8*C + 8*R.
+#include "spmv.cuh"
+
+namespace las2 {
+
+namespace {
+
+constexpr int kShortRow = 32;  // rows up to this many entries inside a tile are summed by one thread
+constexpr int kRowChunk = 1024; // row offsets staged per pass of the reduce phase
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_spmv_stream(const u32 *__restrict__ off, const u32 *__restrict__ idx, const double *__restrict__ val,
+              const u32 *__restrict__ tile_row, const double *__restrict__ x, double *__restrict__ y,
+              double *__restrict__ carry, double *__restrict__ head, u32 rows, u32 nnz) {
+    constexpr int NPT = kSpmvTile / THREADS; // non-zeros per thread
+    static_assert(NPT % 2 == 0, "pairs");
+    __shared__ __align__(16) double prod[kSpmvTile];
+    __shared__ u32 roff[kRowChunk + 1];
+    __shared__ u32 longq[kSpmvTile / kShortRow + 2];
+    __shared__ u32 longn;
+
+    const u32 tile = blockIdx.x;
+    const u32 start = tile * kSpmvTile;
+    const u32 end = min(start + kSpmvTile, nnz);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+
+    const u64 pol_stream = l2_policy_evict_first();
+    const u64 pol_keep = l2_policy_evict_last();
+
+    // ---- phase 1: stream + gather (arrays are zero-padded past nnz, so no bounds checks) ------------
+    {
+        double2 v[NPT / 2];
+        uint2 c[NPT / 2];
+#pragma unroll
+        for (int k = 0; k < NPT / 2; k++) {
+            u32 e = start + 2 * (tid + THREADS * k);
+            v[k] = ld_stream_f64x2(val + e, pol_stream);
+            c[k] = ld_stream_u32x2(idx + e, pol_stream);
+        }
+        double2 xv[NPT / 2];
+#pragma unroll
+        for (int k = 0; k < NPT / 2; k++) {
+            xv[k].x = ld_gather_f64(x + c[k].x, pol_keep);
+            xv[k].y = ld_gather_f64(x + c[k].y, pol_keep);
+        }
+#pragma unroll
+        for (int k = 0; k < NPT / 2; k++) {
+            double2 p;
+            p.x = v[k].x * xv[k].x;
+            p.y = v[k].y * xv[k].y;
+            *reinterpret_cast<double2 *>(&prod[2 * (tid + THREADS * k)]) = p;
+        }
+    }
+
+    // ---- phase 2/3: per-row reduction ------------------------------------------------------------------
+    const u32 R0 = tile_row[tile];
+    const u32 R1 = tile_row[tile + 1];           // row that continues past the tile (or `rows`)
+    const u32 Rlast = (R1 < rows) ? R1 : rows - 1; // last row with a piece (possibly empty) in this tile
+    if (rows == 0) return;
+
+    for (u32 rbase = R0; rbase <= Rlast; rbase += kRowChunk) {
+        const u32 nr = min((u32)kRowChunk, Rlast - rbase + 1);
+        for (u32 i = tid; i <= nr; i += THREADS) roff[i] = off[rbase + i];
+        if (tid == 0) longn = 0;
+        __syncthreads(); // also orders phase 1's shared-memory stores before the reads below
+
+        for (u32 rr = tid; rr < nr; rr += THREADS) {
+            const u32 r = rbase + rr;
+            const u32 o0 = roff[rr], o1 = roff[rr + 1];
+            const u32 lo = max(o0, start) - start;
+            const u32 hi = min(o1, end) - start;
+            if (hi > lo + kShortRow) {
+                longq[atomicAdd(&longn, 1u)] = rr; // queue order is irrelevant to the per-row result
+            } else {
+                double s = 0.0;
+                for (u32 k = lo; k < hi; k++) s += prod[k];
+                if (r == R1) carry[tile] = s;
+                else if (o0 < start) head[tile] = s;
+                else y[r] = s;
+            }
+        }
+        __syncthreads();
+        const u32 nlong = longn;
+        for (u32 qi = warp; qi < nlong; qi += NW) {
+            const u32 rr = longq[qi];
+            const u32 r = rbase + rr;
+            const u32 o0 = roff[rr], o1 = roff[rr + 1];
+            const u32 lo = max(o0, start) - start;
+            const u32 hi = min(o1, end) - start;
+            double s = 0.0;
+            for (u32 k = lo + lane; k < hi; k += 32) s += prod[k];
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (r == R1) carry[tile] = s;
+                else if (o0 < start) head[tile] = s;
+                else y[r] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Rows that straddle tile boundaries: y[r] = carry[b0] + ... + carry[b-1] + head[b], b = the tile the row ends in.
+__global__ void k_spmv_fixup(const u32 *__restrict__ off, const u32 *__restrict__ tile_row,
+                             const double *__restrict__ carry, const double *__restrict__ head,
+                             double *__restrict__ y, u32 num_tiles) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (b >= num_tiles) return;
+    const u32 R0 = tile_row[b], R1 = tile_row[b + 1];
+    const u32 start = b * kSpmvTile;
+    if (R0 < R1) {
+        const u32 o0 = off[R0];
+        if (o0 < start) {
+            double s = 0.0;
+            for (u32 t = o0 / kSpmvTile; t < b; t++) s += carry[t];
+            s += head[b];
+            y[R0] = s;
+        }
+    }
+}
+
+} // namespace
+
+int g_spmv_variant = -1;
+
+void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
+    if (A.rows == 0) return;
+    int variant = g_spmv_variant < 0 ? 0 : g_spmv_variant;
+    switch (variant) {
+    case 1:
+        k_spmv_stream<128><<<A.num_tiles, 128, 0, s>>>(A.off, A.idx, A.val, A.tile_row, x, y, A.carry, A.head,
+                                                       (u32)A.rows, (u32)A.nnz);
+        break;
+    case 2:
+        k_spmv_stream<512><<<A.num_tiles, 512, 0, s>>>(A.off, A.idx, A.val, A.tile_row, x, y, A.carry, A.head,
+                                                       (u32)A.rows, (u32)A.nnz);
+        break;
+    default:
+        k_spmv_stream<256><<<A.num_tiles, 256, 0, s>>>(A.off, A.idx, A.val, A.tile_row, x, y, A.carry, A.head,
+                                                       (u32)A.rows, (u32)A.nnz);
+        break;
+    }
+    if (A.num_tiles > 1) {
+        k_spmv_fixup<<<cdiv(A.num_tiles - 1, 128), 128, 0, s>>>(A.off, A.tile_row, A.carry, A.head, y, A.num_tiles);
+        if (launches) *launches += 1;
+    }
+    LAS2_LAUNCH_CHECK();
+    if (launches) *launches += 1;
+}
+
+} // namespace las2

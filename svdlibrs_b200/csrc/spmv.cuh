@@ -1,0 +1,12 @@
+// spmv.cuh -- sparse mat-vec entry points (see spmv.cu).
+#pragma once
+#include "device_csr.cuh"
+
+namespace las2 {
+
+extern int g_spmv_variant; // -1 auto; test / tuning override (svdlas2_operator_set "spmv_variant")
+
+// y = A x on stream s.  x: A.cols doubles, y: A.rows doubles, both device-resident, no aliasing.
+void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches = nullptr);
+
+} // namespace las2

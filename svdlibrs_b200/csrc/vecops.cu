@@ -1,0 +1,169 @@
+// vecops.cu -- fused, deterministic BLAS-1 kernels (see vecops.cuh for the conventions).
+// All kernels are HBM/L2-bound streams over N-vectors: 128-bit loads, grid capped at 4 CTAs per SM.
+#include "vecops.cuh"
+
+namespace las2 {
+
+namespace {
+
+// Canonical sum of n per-CTA partials: warp 0, lane-strided sequential adds, then a shuffle tree.
+// Every kernel that needs the scalar calls exactly this, so all of them see the same bits.
+__device__ __forceinline__ double cta_sum_partials(const double *__restrict__ p, int n, double *smem1) {
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += 32) s += p[i];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) *smem1 = s;
+    }
+    __syncthreads();
+    return *smem1;
+}
+
+__device__ __forceinline__ double cta_reduce(double v, double *smem /* >= blockDim/32 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 0; w < nw; w++) s += smem[w];
+    }
+    return s; // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_scale(double2 *__restrict__ dst, const double2 *__restrict__ src,
+                                                       double alpha, u64 n2) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n2; i += stride) {
+        double2 v = src[i];
+        v.x = __dmul_rn(alpha, v.x);
+        v.y = __dmul_rn(alpha, v.y);
+        dst[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_dot(const double2 *__restrict__ a, const double2 *__restrict__ b,
+                                                     u64 n2, double *__restrict__ out) {
+    __shared__ double sm[kVecThreads / 32];
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (; i < n2; i += stride) {
+        double2 av = a[i], bv = b[i];
+        acc = fma(av.x, bv.x, acc);
+        acc = fma(av.y, bv.y, acc);
+    }
+    double s = cta_reduce(acc, sm);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// r -= coef * x ; partial of r . y (y == nullptr -> r . r ; DOT == false -> no reduction at all)
+template <bool DOT>
+__global__ void __launch_bounds__(kVecThreads)
+k_axpy_dot(double2 *__restrict__ r, const double2 *__restrict__ x, Coef coef, const double2 *__restrict__ y, u64 n2,
+           double *__restrict__ out) {
+    __shared__ double sm[kVecThreads / 32];
+    __shared__ double cs;
+    const double c = coef.parts ? cta_sum_partials(coef.parts, coef.nparts, &cs) : coef.imm;
+    const double nc = -c;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (; i < n2; i += stride) {
+        double2 rv = r[i];
+        const double2 xv = x[i];
+        rv.x = __dadd_rn(rv.x, __dmul_rn(nc, xv.x)); // y += da * x with da = -t, as svd_daxpy(-t, x, y)
+        rv.y = __dadd_rn(rv.y, __dmul_rn(nc, xv.y));
+        r[i] = rv;
+        if (DOT) {
+            double2 yv;
+            if (y == nullptr) yv = rv;
+            else if (y == x) yv = xv;
+            else yv = y[i];
+            acc = fma(rv.x, yv.x, acc);
+            acc = fma(rv.y, yv.y, acc);
+        }
+    }
+    if (DOT) {
+        double s = cta_reduce(acc, sm);
+        if (threadIdx.x == 0) out[blockIdx.x] = s;
+    }
+}
+
+// sigma = sqrt(t), u *= 1/sigma  (ritvec tail, src/lib.rs:1851, 1858); t arrives as partials
+__global__ void __launch_bounds__(kVecThreads)
+k_sigma_scale(double *__restrict__ u, u64 m, const double *__restrict__ parts, int nparts, double *__restrict__ sigma_out) {
+    __shared__ double ts;
+    const double t = cta_sum_partials(parts, nparts, &ts);
+    const double sigma = sqrt(t);
+    const double inv = 1.0 / sigma;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sigma_out = sigma;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) u[i] = __dmul_rn(u[i], inv);
+}
+
+__global__ void k_gather_scalars(GatherList g, double *__restrict__ out) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < g.count) {
+        double s = 0.0;
+        const double *p = g.parts[w];
+        const int n = g.nparts[w];
+        for (int i = lane; i < n; i += 32) s += p[i];
+        s = warp_sum(s);
+        if (lane == 0) out[w] = s;
+    }
+}
+
+} // namespace
+
+unsigned vec_grid(u64 ld) {
+    u64 n2 = ld / 2;
+    u64 g = (n2 + (u64)kVecThreads * 2 - 1) / ((u64)kVecThreads * 2); // ~2 double2 per thread before striding
+    if (g < 1) g = 1;
+    if (g > (u64)kMaxParts) g = kMaxParts;
+    return (unsigned)g;
+}
+
+void vec_scale(double *dst, const double *src, double alpha, u64 ld, cudaStream_t s) {
+    k_scale<<<vec_grid(ld), kVecThreads, 0, s>>>((double2 *)dst, (const double2 *)src, alpha, ld / 2);
+    LAS2_LAUNCH_CHECK();
+}
+
+void vec_dot(const double *a, const double *b, u64 ld, PartialSlot &out, cudaStream_t s) {
+    unsigned g = vec_grid(ld);
+    k_dot<<<g, kVecThreads, 0, s>>>((const double2 *)a, (const double2 *)b, ld / 2, out.parts);
+    out.nparts = (int)g;
+    LAS2_LAUNCH_CHECK();
+}
+
+void vec_axpy_dot(double *r, const double *x, Coef coef, const double *y, u64 ld, PartialSlot &out, cudaStream_t s) {
+    unsigned g = vec_grid(ld);
+    k_axpy_dot<true><<<g, kVecThreads, 0, s>>>((double2 *)r, (const double2 *)x, coef, (const double2 *)y, ld / 2,
+                                               out.parts);
+    out.nparts = (int)g;
+    LAS2_LAUNCH_CHECK();
+}
+
+void vec_axpy(double *r, const double *x, Coef coef, u64 ld, cudaStream_t s) {
+    k_axpy_dot<false><<<vec_grid(ld), kVecThreads, 0, s>>>((double2 *)r, (const double2 *)x, coef, nullptr, ld / 2,
+                                                           nullptr);
+    LAS2_LAUNCH_CHECK();
+}
+
+void vec_sigma_scale(double *u, u64 m, const PartialSlot &t, double *sigma_out, cudaStream_t s) {
+    u64 g = (m + kVecThreads * 4 - 1) / (kVecThreads * 4);
+    if (g < 1) g = 1;
+    if (g > (u64)kMaxParts) g = kMaxParts;
+    k_sigma_scale<<<(unsigned)g, kVecThreads, 0, s>>>(u, m, t.parts, t.nparts, sigma_out);
+    LAS2_LAUNCH_CHECK();
+}
+
+void gather_scalars(const GatherList &g, double *out, cudaStream_t s) {
+    k_gather_scalars<<<1, 32 * 8, 0, s>>>(g, out);
+    LAS2_LAUNCH_CHECK();
+}
+
+} // namespace las2

@@ -1,0 +1,78 @@
+// vecops.cuh -- fused BLAS-1 on the device-resident Lanczos vectors, and the blocked panel operations.
+//
+// Replaces the reference's svd_daxpy / svd_ddot / svd_norm / svd_datx / svd_dscal loops
+// (src/lib.rs:840-844, 893-914) as they are chained in stpone (:1187-1198), lanczos_step (:1274-1304),
+// purge (:1372-1388) and startv (:1132-1144).
+//
+// Conventions
+//  * every N-vector is allocated with `ld` = N rounded up to 32 doubles and its padding is kept at 0.0,
+//    so kernels run over ld/2 double2 elements without tail handling;
+//  * reductions are two-stage and deterministic: each CTA writes one partial (fixed-order shuffle tree),
+//    and whoever needs the scalar sums the partials again with one fixed-order warp reduction
+//    (cta_sum_partials) -- producers and consumers therefore agree bit for bit, on every GPU of a
+//    replicated multi-GPU run, with no atomics;
+//  * element-wise updates use separate multiply and add (no FMA contraction), as the Rust reference does.
+#pragma once
+
+#include "util.cuh"
+
+namespace las2 {
+
+constexpr int kVecThreads = 256;
+constexpr int kMaxParts = 592; // 148 SMs x 4: upper bound on the grid of any reducing kernel
+
+// A scalar that is either known on the host (imm) or still sitting in HBM as per-CTA partial sums.
+struct Coef {
+    const double *parts;
+    int nparts;
+    double imm;
+    static Coef value(double v) { return Coef{nullptr, 0, v}; }
+    static Coef partials(const double *p, int n) { return Coef{p, n, 0.0}; }
+};
+
+struct PartialSlot {
+    double *parts; // kMaxParts doubles
+    int nparts;    // set by the producing launch
+};
+
+unsigned vec_grid(u64 ld);
+
+// dst = alpha * src                                   (svd_datx / svd_dscal, :903-914)
+void vec_scale(double *dst, const double *src, double alpha, u64 ld, cudaStream_t s);
+// out = a . b                                         (svd_ddot, :893-895)
+void vec_dot(const double *a, const double *b, u64 ld, PartialSlot &out, cudaStream_t s);
+// r -= coef * x ;  out = r . y   (y == nullptr: out = r . r)       (svd_daxpy + svd_ddot pairs)
+void vec_axpy_dot(double *r, const double *x, Coef coef, const double *y, u64 ld, PartialSlot &out, cudaStream_t s);
+// r -= coef * x                                       (svd_daxpy, :840-844)
+void vec_axpy(double *r, const double *x, Coef coef, u64 ld, cudaStream_t s);
+
+// Sum up to 8 partial slots with the canonical reduction and write the scalars to `out` (pinned host memory
+// or device memory).
+struct GatherList {
+    const double *parts[8];
+    int nparts[8];
+    int count;
+};
+void gather_scalars(const GatherList &g, double *out, cudaStream_t s);
+
+// ---- panel operations on Q (column-major, leading dimension ld), columns [col0, col0+ncols) ----------
+// Classical Gram-Schmidt sweep of the pair (a, b) against the stored Lanczos vectors, as purge performs it
+// with its frozen snapshots w3/w4 (src/lib.rs:1374-1382):
+//      ca = Q'a, cb = Q'b ;  a -= Q ca, b -= Q cb ;  sum|ca|, sum|cb| ;  dot_out = a . b (updated)
+// b may be nullptr (single right-hand side: the restart sweep of startv, :1132-1135).
+struct PanelWork {
+    DevBuf<double> partials; // row-block partial dots
+    DevBuf<double> coeffs;   // 2 * ncols
+    DevBuf<double> dotparts; // one per update CTA when that exceeds kMaxParts
+    size_t cap_cols = 0, cap_blocks = 0;
+};
+// abs_a / abs_b receive the partials of sum|ca| / sum|cb| ; dot_out (optional, needs b) those of a . b.
+void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, double *b, PanelWork &work,
+                PartialSlot *abs_a, PartialSlot *abs_b, PartialSlot *dot_out, cudaStream_t s, u64 *launches);
+
+// Ritz back-transform (ritvec, src/lib.rs:1807-1817): V[:, c] = sum_k Q[:, k] * C[k, c], k < js, c < d.
+// C is js x d row-major on the device; V is column-major with leading dimension ld (each Ritz vector contiguous).
+void ritz_contract(const double *Q, u64 ld, u64 n, u32 js, const double *C, u32 d, double *V, cudaStream_t s,
+                   u64 *launches);
+
+} // namespace las2

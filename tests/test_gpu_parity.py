@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libsvdlas2_b200.so), against the CPU oracle
+on the same matrix and seed.  Mirrors the reference's own tests (src/lib.rs:2136-2237 and the doctests :26-283)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import assert_svd_parity, orthonormality_defect
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_M = np.array([[1, 16, 49], [4, 25, 64], [9, 36, 81]], dtype=float)
+GOLDEN_S = [123.67657874254405, 6.084527896513759, 0.2870380041828973]
+GOLDEN_UT = [[-0.4152068408862081, -0.556377565193878, -0.719755016814907],
+             [-0.7534435856189199, -0.23308021364108839, 0.6148140997884891],
+             [-0.5098294249756481, 0.7975698207417085, -0.3224226084985998]]
+GOLDEN_VT = [[-0.07372869095916511, -0.3756889918994792, -0.9238083467337805],
+             [0.6323518477280158, 0.6986910001499903, -0.33460727276072516],
+             [-0.7711648467120451, 0.6088420712097343, -0.18605405537270261]]
+
+
+def test_golden_3x3_seed_3141(las2):
+    """doctest src/lib.rs:172-233 + documented output :238-283"""
+    r = las2.svd_dim_seed(sp.csc_matrix(GOLDEN_M), 0, 3141)
+    assert r.d == 3 and r.ut.shape == (3, 3) and r.vt.shape == (3, 3) and r.s.shape == (3,)
+    eps = 1.0e-12
+    assert np.abs(r.recompose() - GOLDEN_M).max() < eps * 100  # entries up to 81: 1e-12 relative to scale
+    assert np.abs(r.s - np.array(GOLDEN_S)).max() < eps * 124
+    # same signs and digits as the documented output (to 1e-12; the CPU oracle matches it bit for bit)
+    assert np.abs(r.ut - np.array(GOLDEN_UT)).max() < 1e-11
+    assert np.abs(r.vt - np.array(GOLDEN_VT)).max() < 1e-11
+    g = r.diagnostics
+    assert (g.non_zero, g.dimensions, g.iterations, g.transposed, g.lanczos_steps, g.ritz_values_stabilized,
+            g.significant_values, g.singular_values, g.random_seed) == (9, 3, 3, False, 3, 3, 3, 3, 3141)
+    assert g.end_interval == [-1e-30, 1e-30] and g.kappa == 1e-6
+
+
+def test_basic_2x2(las2):
+    """src/lib.rs:2183-2214 (random seed: the answer is seed independent)"""
+    A = sp.coo_matrix(([4.0, 3.0, -5.0], ([0, 1, 1], [0, 0, 1])), shape=(2, 2))
+    r = las2.svd(A)
+    assert r.d == 2 == r.ut.shape[0] == r.vt.shape[0] == r.s.shape[0]
+    assert np.abs(r.recompose() - A.toarray()).max() < 1e-12
+    assert abs(r.s[0] - 6.3245553203368) < 1e-12 and abs(r.s[1] - 3.1622776601684) < 1e-12
+
+
+def test_identity_3x3(las2):
+    """src/lib.rs:2216-2236: degenerate spectrum -> restart path, one copy of the repeated sigma"""
+    r = las2.svd(sp.csc_matrix(np.eye(3)))
+    assert r.d == 1 and abs(r.s[0] - 1.0) < 1e-12
+    assert r.diagnostics.lanczos_steps == 2 and r.diagnostics.ritz_values_stabilized == 1
+
+
+def test_coo_csc_csr_identical(las2):
+    """src/lib.rs:2159-2166: exact equality of the whole result across input formats"""
+    coo = sp.coo_matrix(([3.0, 4.0], ([1, 2], [0, 1])), shape=(4, 4))
+    a = las2.svd_dim_seed(coo, 3, 12345)
+    b = las2.svd_dim_seed(coo.tocsc(), 3, 12345)
+    c = las2.svd_dim_seed(coo.tocsr(), 3, 12345)
+    assert a == b and b == c
+    assert a.d == 2 and np.allclose(a.s, [4.0, 3.0], atol=1e-12) and a.diagnostics.lanczos_steps == 2
+
+
+def test_recompose_is_ut_s_vt(las2):
+    """src/lib.rs:2168-2181"""
+    r = las2.svd(sp.coo_matrix(GOLDEN_M))
+    assert np.array_equal(r.recompose(), r.ut.T @ np.diag(r.s) @ r.vt)
+
+
+def test_quickstart_doctests(las2):
+    """src/lib.rs:26-70: the three convenience calls return Ok on CSR 2x2, CSC 3x3 (dim 3), COO 3x3 (seed 12345)"""
+    A2 = sp.coo_matrix(([1.0, 3.0, -5.0], ([0, 1, 1], [0, 0, 1])), shape=(2, 2)).tocsr()
+    assert las2.svd(A2).d == 2
+    assert las2.svd_dim(sp.csc_matrix(GOLDEN_M), 3).d == 3
+    assert las2.svd_dim_seed(sp.coo_matrix(GOLDEN_M), 3, 12345).d == 3
+
+
+def test_errors_match_reference(las2):
+    with pytest.raises(las2.SvdLibError) as e:
+        las2.svd(sp.csr_matrix(np.ones((1, 5))))
+    assert e.value.kind == "Las2Error" and "insufficient dimensions: 1" in str(e.value)
+    with pytest.raises(las2.SvdLibError) as e:  # exactly rank 1: the reference panics in error_bound (:1489)
+        las2.svd(sp.csr_matrix(np.ones((3, 3))))
+    assert e.value.kind == "ReferencePanic"
+    with pytest.raises(las2.SvdLibError) as e:  # all-zero matrix: startv cannot find a vector in range (:1128)
+        las2.svd_dim_seed(sp.csr_matrix((4, 4)), 2, 7)
+    assert e.value.kind == "StartvError"
+
+
+def test_malformed_arrays_are_rejected(las2):
+    A = sp.csr_matrix(GOLDEN_M)
+    bad = sp.csr_matrix(GOLDEN_M)
+    bad.indices = bad.indices.copy()
+    bad.indices[4] = 7  # column out of range
+    with pytest.raises(las2.SvdLibError) as e:
+        las2.svd(bad)
+    assert e.value.kind == "InvalidArgument"
+    assert las2.svd(A).d == 3  # the library is still usable afterwards
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc", "coo"])
+@pytest.mark.parametrize("shape", [(300, 200), (200, 300), (257, 255)])
+def test_opa_opb_against_oracle(las2, oracle, fmt, shape):
+    """SMat::svd_opa (:2035-2130) and svd_opb (:829-837): element-wise agreement to 1e-13 norm-wise"""
+    rng = np.random.default_rng(7)
+    A = sp.random(*shape, density=0.05, format=fmt, random_state=rng)
+    op = las2.Operator(A)
+    for transposed in (False, True):
+        x = rng.standard_normal(shape[0] if transposed else shape[1])
+        y = op.opa(x, transposed)
+        y0 = oracle.opa(A, x, transposed)
+        assert np.linalg.norm(y - y0) <= 1e-13 * np.linalg.norm(y0)
+    x = rng.standard_normal(op.n)
+    y0 = oracle.opb(A, x, op.transposed)
+    y = op.opb(x)
+    assert op.transposed == (shape[1] >= 1.2 * shape[0])
+    assert np.linalg.norm(y - y0) <= 1e-13 * np.linalg.norm(y0)
+    op.close()
+
+
+def test_coo_duplicates_are_summed(las2, oracle):
+    """CooMatrix may hold duplicates; each triplet contributes (src/lib.rs:2121-2127)"""
+    rng = np.random.default_rng(3)
+    n = 4000
+    row = rng.integers(0, 60, n); col = rng.integers(0, 40, n); val = rng.standard_normal(n)
+    A = sp.coo_matrix((val, (row, col)), shape=(60, 40))
+    assert A.nnz == n  # scipy keeps duplicates in COO
+    op = las2.Operator(A)
+    x = rng.standard_normal(40)
+    assert np.linalg.norm(op.opa(x) - oracle.opa(A, x)) <= 1e-13 * np.linalg.norm(oracle.opa(A, x))
+    op.close()
+    got, ref = las2.svd_dim_seed(A, 10, 99), oracle.svd_dim_seed(A, 10, 99)
+    assert_svd_parity(got, ref)
+
+
+def test_spmv_ragged_rows(las2, oracle):
+    """rows of length 0, 1 and > one nnz-tile, leading / trailing empty rows, tile-straddling rows"""
+    rng = np.random.default_rng(11)
+    nrows, ncols = 700, 9000
+    lens = np.zeros(nrows, dtype=int)
+    lens[5] = 9000; lens[6] = 1; lens[7] = 5000; lens[300:310] = 33; lens[310:340] = 32; lens[400] = 4097
+    lens[500:650] = rng.integers(0, 60, 150)
+    rows, cols = [], []
+    for i, l in enumerate(lens):
+        c = np.sort(rng.choice(ncols, size=l, replace=False))
+        rows.append(np.full(l, i)); cols.append(c)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    A = sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(nrows, ncols))
+    op = las2.Operator(A)  # wide -> transposed orientation; both SpMV directions get exercised
+    for transposed in (False, True):
+        x = rng.standard_normal(nrows if transposed else ncols)
+        y, y0 = op.opa(x, transposed), oracle.opa(A, x, transposed)
+        assert np.linalg.norm(y - y0) <= 1e-13 * np.linalg.norm(y0)
+        assert np.array_equal(y == 0, y0 == 0)
+    op.close()
+
+
+@pytest.mark.parametrize("shape,dims,seed", [((400, 300), 10, 12345), ((300, 400), 25, 12345), ((1500, 400), 10, 1),
+                                             ((50, 50), 0, 3141), ((800, 600), 25, 12345)])
+def test_random_sparse_parity(las2, oracle, shape, dims, seed):
+    rng = np.random.default_rng(seed)
+    A = sp.random(*shape, density=0.03, format="csr", random_state=rng)
+    got, ref = las2.svd_dim_seed(A, dims, seed), oracle.svd_dim_seed(A, dims, seed)
+    assert_svd_parity(got, ref)
+    assert orthonormality_defect(got.vt) < 1e-9
+
+
+def test_wide_csc_transposed_path(las2, oracle):
+    """cfg 3 in miniature: CSC input with cols >= 1.2 rows -> internal transpose, ut/vt swapped back (:631-633)"""
+    from svdlibrs_b200 import synthetic
+    A, dims = synthetic.make("cfg3", scale=0.002)
+    assert A.format == "csc" and A.shape[1] >= 1.2 * A.shape[0]
+    got, ref = las2.svd_dim_seed(A, 20, 12345), oracle.svd_dim_seed(A, 20, 12345)
+    assert got.diagnostics.transposed and got.ut.shape[1] == A.shape[0] and got.vt.shape[1] == A.shape[1]
+    assert_svd_parity(got, ref)
+
+
+def test_powerlaw_parity(las2, oracle):
+    """cfg 2 in miniature (power-law rows and columns)"""
+    from svdlibrs_b200 import synthetic
+    A, _ = synthetic.make("cfg2", scale=0.02)
+    got, ref = las2.svd_dim_seed(A, 30, 12345), oracle.svd_dim_seed(A, 30, 12345)
+    assert_svd_parity(got, ref)
+    resid = np.linalg.norm(A @ got.vt[0] - got.s[0] * got.ut[0])
+    assert resid <= 1e-9 * got.s[0]
+
+
+def test_cfg1_full_size_parity(las2, oracle):
+    """BASELINE configs[0] at full size: 50,000 x 10,000, 5e5 nnz, dims 20, seed 12345 (oracle: ~6 s on one core)"""
+    from svdlibrs_b200 import synthetic
+    A, dims = synthetic.make("cfg1")
+    got, ref = las2.svd_dim_seed(A, dims, 12345), oracle.svd_dim_seed(A, dims, 12345)
+    assert_svd_parity(got, ref)
+    # Lanczos recurrence agrees step by step while it is well conditioned
+    k = 30
+    assert np.allclose(got.trace["alf"][:k], ref.trace["alf"][:k], rtol=1e-9)
+    assert np.allclose(got.trace["bet"][1:k], ref.trace["bet"][1:k], rtol=1e-9)
+
+
+def test_operator_is_reusable_and_deterministic(las2):
+    from svdlibrs_b200 import synthetic
+    A, _ = synthetic.make("cfg2", scale=0.01)
+    with las2.Operator(A) as op:
+        a = op.solve(20, random_seed=5)
+        b = op.solve(20, random_seed=5)
+    c = las2.svd_dim_seed(A, 20, 5)
+    assert a == b and a == c  # bit-identical: no atomics, fixed-order reductions
+
+
+def test_iterations_and_kappa_parameters(las2, oracle):
+    rng = np.random.default_rng(5)
+    A = sp.random(500, 300, density=0.05, format="csr", random_state=rng)
+    got = las2.svdLAS2(A, 10, 40, (-1e-30, 1e-30), 1e-4, 77)
+    ref = oracle.svd_las2(A, 10, 40, (-1e-30, 1e-30), 1e-4, 77)
+    assert got.diagnostics.iterations == 40
+    assert_svd_parity(got, ref)
