@@ -1,0 +1,34 @@
+/*
+ * include/svdlas2_testing.h -- test hooks into the HOST-side logic of libsvdlas2_b200.so (no GPU needed).
+ * They exist so that the CPU test-suite can compare the product's control-flow arithmetic with the oracle bit
+ * for bit; they are not part of the drop-in boundary (include/svdlas2.h).
+ */
+#ifndef SVDLAS2_TESTING_H
+#define SVDLAS2_TESTING_H
+#include "svdlas2.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* first n samples of StdRng(seed).gen_range(-1.0..1.0)  (reference src/lib.rs:1109-1114) */
+SVDLAS2_API void svdlas2_test_start_vector(uint32_t seed, uint64_t n, double *out);
+/* svd_pythag (src/lib.rs:873-890) */
+SVDLAS2_API double svdlas2_test_hypot(double a, double b);
+/* imtqlb (src/lib.rs:962-1068): d, e, bnd overwritten; returns a status code */
+SVDLAS2_API int svdlas2_test_ql_values(uint64_t n, double *d, double *e, double *bnd);
+/* imtql2 (src/lib.rs:1576-1693) through the rotation plan: d, e overwritten, z (n x n row-major) receives the
+ * eigenvectors exactly as the reference's in-place update of an identity would (rotations replayed on the CPU
+ * here; the product replays the same plan on the GPU).  n_rotations / n_sweeps are optional outputs. */
+SVDLAS2_API int svdlas2_test_ql_vectors(uint64_t n, double *d, double *e, double *z, uint64_t *n_rotations,
+                                        uint64_t *n_sweeps);
+/* error_bound (src/lib.rs:1480-1532): returns status; neig and the updated enough flag through pointers */
+SVDLAS2_API int svdlas2_test_refine_bounds(int *enough, double endl, double endr, double *ritz, double *bnd,
+                                           uint64_t step, double tol, uint64_t *neig);
+/* insert_sort (src/lib.rs:815-825) */
+SVDLAS2_API void svdlas2_test_cosort(uint64_t n, double *keys, double *vals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["svd", "svd_dim", "svd_dim_seed", "svdLAS2", "SvdRec", "Diagnostics", "SvdLibError", "Operator",
+__all__ = ["svd", "svd_dim", "svd_dim_seed", "svdLAS2", "SvdRec", "Diagnostics", "SvdLibError", "Operator", "RawMatrix",
            "ShardedOperator", "comm_unique_id", "build"]
 
 build = _lib.build
@@ -93,7 +93,25 @@ class SvdRec:
 # ------------------------------------------------------------------------------------------------ helpers
 
 def _u64(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype == np.int64 and a.flags.c_contiguous:
+        return a.view(np.uint64)  # non-negative by construction: reinterpret, do not copy
     return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class RawMatrix:
+    """The raw arrays of a nalgebra-sparse matrix (u64 indices), borrowed without conversion:
+    RawMatrix("csr", (nrows, ncols), row_offsets, col_indices, values)   -- CsrMatrix::csr_data()
+    RawMatrix("csc", (nrows, ncols), col_offsets, row_indices, values)   -- CscMatrix::csc_data()
+    RawMatrix("coo", (nrows, ncols), row_indices, col_indices, values)   -- CooMatrix triplets"""
+
+    def __init__(self, format: str, shape, a, b, data):
+        self.format, self.shape, self.data = format, tuple(shape), data
+        self.nnz = int(len(data))
+        if format == "coo":
+            self.row, self.col = a, b
+        else:
+            self.indptr, self.indices = a, b
 
 
 def _f64(a) -> np.ndarray:
@@ -122,35 +140,50 @@ def _raise(code: int):
     raise SvdLibError(code, _lib.lib().svdlas2_last_error().decode(errors="replace"))
 
 
+class _ResultOwner:
+    """Keeps a svdlas2_result alive while numpy arrays view its (pinned, library-owned) buffers; the buffers go
+    back to the library's host pool when the last view is garbage collected (no 0.9 GB memcpy at cfg 2)."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr is not None:
+                _lib.lib().svdlas2_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _view(owner: _ResultOwner, p, shape) -> np.ndarray:
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape)
+    buf = (C.c_double * n).from_address(C.addressof(p.contents))
+    buf._owner = owner  # the ctypes array is the numpy base object; it pins the owner
+    return np.frombuffer(buf, dtype=np.float64).reshape(shape)
+
+
 def _take_result(ptr) -> SvdRec:
-    L = _lib.lib()
-    try:
-        r = ptr.contents
-        d = int(r.d)
-
-        def mat(p, cols):
-            if d == 0 or cols == 0:
-                return np.zeros((d, int(cols)))
-            return np.ctypeslib.as_array(p, shape=(d, int(cols))).copy()
-
-        ut, vt = mat(r.ut, r.ut_cols), mat(r.vt, r.vt_cols)
-        s = np.ctypeslib.as_array(r.s, shape=(d,)).copy() if d else np.zeros(0)
-        g = r.diagnostics
-        diag = Diagnostics(int(g.non_zero), int(g.dimensions), int(g.iterations), bool(g.transposed),
-                           int(g.lanczos_steps), int(g.ritz_values_stabilized), int(g.significant_values),
-                           int(g.singular_values), [g.end_interval[0], g.end_interval[1]], float(g.kappa),
-                           int(g.random_seed))
-        prof = {name: getattr(r.profile, name) for name, _ in _lib.Profile._fields_}
-        n = int(r.trace_len)
-        trace = {}
-        if n and r.alf:
-            trace = dict(alf=np.ctypeslib.as_array(r.alf, shape=(n,)).copy(),
-                         bet=np.ctypeslib.as_array(r.bet, shape=(n + 1,)).copy(),
-                         ritz=np.ctypeslib.as_array(r.ritz, shape=(n,)).copy(),
-                         bnd=np.ctypeslib.as_array(r.bnd, shape=(n,)).copy())
-        return SvdRec(d, ut, s, vt, diag, prof, trace)
-    finally:
-        L.svdlas2_free(ptr)
+    owner = _ResultOwner(ptr)
+    r = ptr.contents
+    d = int(r.d)
+    ut = _view(owner, r.ut, (d, int(r.ut_cols)))
+    vt = _view(owner, r.vt, (d, int(r.vt_cols)))
+    s = _view(owner, r.s, (d,)).copy()
+    g = r.diagnostics
+    diag = Diagnostics(int(g.non_zero), int(g.dimensions), int(g.iterations), bool(g.transposed),
+                       int(g.lanczos_steps), int(g.ritz_values_stabilized), int(g.significant_values),
+                       int(g.singular_values), [g.end_interval[0], g.end_interval[1]], float(g.kappa),
+                       int(g.random_seed))
+    prof = {name: getattr(r.profile, name) for name, _ in _lib.Profile._fields_}
+    n = int(r.trace_len)
+    trace = {}
+    if n and r.alf:
+        trace = dict(alf=_view(owner, r.alf, (n,)).copy(), bet=_view(owner, r.bet, (n + 1,)).copy(),
+                     ritz=_view(owner, r.ritz, (n,)).copy(), bnd=_view(owner, r.bnd, (n,)).copy())
+    return SvdRec(d, ut, s, vt, diag, prof, trace)
 
 
 # ------------------------------------------------------------------------------------------------ public API
@@ -281,7 +314,7 @@ class ShardedOperator(Operator):
                  comm_id: Optional[bytes], b_is_a_transposed: bool = False, device: int = -1):
         L = _lib.lib()
         if getattr(local_csr, "format", None) != "csr":
-            raise TypeError("the shard must be a scipy.sparse csr matrix holding rows [row_begin, row_end) of B")
+            raise TypeError("the shard must be a csr matrix holding rows [row_begin, row_end) of B")
         rows, n = local_csr.shape
         a, b, v = _u64(local_csr.indptr), _u64(local_csr.indices), _f64(local_csr.data)
         idbuf = (C.c_uint8 * _lib.COMM_ID_BYTES)(*(comm_id or bytes(_lib.COMM_ID_BYTES)))

@@ -4,6 +4,7 @@
 #include <new>
 #include <string>
 
+#include "host_pool.hpp"
 #include "las2.hpp"
 #include "spmv.cuh"
 
@@ -138,7 +139,8 @@ int svdlas2_coo(uint64_t nrows, uint64_t ncols, uint64_t nnz, const uint64_t *ro
 
 void svdlas2_free(svdlas2_result *r) {
     if (!r) return;
-    std::free(r->ut); std::free(r->s); std::free(r->vt);
+    host_release(r->ut); host_release(r->vt); // pinned pool (falls back to free() for foreign pointers)
+    std::free(r->s);
     std::free(r->alf); std::free(r->bet); std::free(r->ritz); std::free(r->bnd);
     std::free(r);
 }

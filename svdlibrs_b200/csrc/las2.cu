@@ -18,10 +18,12 @@
 #include "las2.hpp"
 
 #include <chrono>
+#include <future>
 #include <cmath>
 #include <cstring>
 #include <string>
 
+#include "host_pool.hpp"
 #include "spmv.cuh"
 #include "tridiag_device.cuh"
 
@@ -59,6 +61,10 @@ struct Solver {
     std::vector<double> alf, bet, eta, oldeta, ritz, bnd, w5;
     svdlas2_profile prof;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> opb_events;
+    // result buffers (pinned, from the host pool) are acquired on a helper thread while the GPU runs lanso
+    cudaStream_t copy_stream = nullptr;
+    std::future<void *> fut_m, fut_n; // dims x M and dims x N doubles
+    bool prefetched = false;
 
     Solver(Operator &o, u64 dimensions, u64 iterations)
         : op(o), s(o.stream), N(o.N), M(o.M), ld(round_up(o.N, 32)), dims(dimensions), iters(iterations),
@@ -74,9 +80,22 @@ struct Solver {
         bet.assign(iters + 1, 0.0); ritz.assign(iters + 1, 0.0);
         bnd.assign(iters + 1, 1.7976931348623157e308); // f64::MAX, :775
         w5.assign(iters + 2, 0.0);
+        LAS2_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        const u64 want = dims * (M + N) * sizeof(double);
+        if (want <= ((u64)8 << 30)) { // only when the upper bound d <= dims is affordable
+            const int dev = op.device;
+            const size_t bm = std::max<u64>(1, dims * M) * sizeof(double), bn = std::max<u64>(1, dims * N) * sizeof(double);
+            fut_m = std::async(std::launch::async, [dev, bm] { cudaSetDevice(dev); return host_acquire(bm); });
+            fut_n = std::async(std::launch::async, [dev, bn] { cudaSetDevice(dev); return host_acquire(bn); });
+            prefetched = true;
+        }
     }
     ~Solver() {
         for (auto &e : opb_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        // buffers nobody took (an error before ritvec) go back to the pool
+        try { if (fut_m.valid()) host_release(fut_m.get()); } catch (...) {}
+        try { if (fut_n.valid()) host_release(fut_n.get()); } catch (...) {}
     }
 
     double *q(u64 j) { return Q.get() + j * ld; }
@@ -380,10 +399,13 @@ struct Solver {
         res->diagnostics.singular_values = nsig;   // sic, :649
 
         const u64 mcols = M, ncols = N;
-        double *hV = (double *)std::malloc(std::max<size_t>(1, d * ncols) * sizeof(double));
-        double *hU = (double *)std::malloc(std::max<size_t>(1, d * mcols) * sizeof(double));
+        double *hU = (double *)(prefetched ? fut_m.get() : host_acquire(std::max<u64>(1, d * mcols) * sizeof(double)));
+        double *hV = nullptr;
+        try {
+            hV = (double *)(prefetched ? fut_n.get() : host_acquire(std::max<u64>(1, d * ncols) * sizeof(double)));
+        } catch (...) { host_release(hU); throw; }
         double *hS = (double *)std::malloc(std::max<size_t>(1, d) * sizeof(double));
-        if (!hV || !hU || !hS) { std::free(hV); std::free(hU); std::free(hS); throw Error(SVDLAS2_ERR_ALLOC, "host result allocation failed"); }
+        if (!hS) { host_release(hU); host_release(hV); throw Error(SVDLAS2_ERR_ALLOC, "host result allocation failed"); }
         // hand ownership to the result right away so that an exception below cannot leak
         const bool tr = op.transposed;
         res->ut = tr ? hV : hU; res->ut_cols = tr ? ncols : mcols;
@@ -406,6 +428,14 @@ struct Solver {
         qcap = qused = 0;
 
         // sigma_i = sqrt(v_i . B'B v_i), u_i = B v_i / sigma_i (:1839-1859).  B v_i is computed once and reused.
+        // Finished rows stream to the (pinned) result on a second stream while later rows are still computed.
+        cudaEvent_t ev;
+        LAS2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } evdel{ev};
+        LAS2_CUDA(cudaEventRecord(ev, s));
+        LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+        LAS2_CUDA(cudaMemcpy2DAsync(hV, ncols * sizeof(double), V.get(), ld * sizeof(double), ncols * sizeof(double), d,
+                                    cudaMemcpyDeviceToHost, copy_stream));
         DevBuf<double> U((size_t)d * mcols);
         DevBuf<double> S(d);
         for (u64 i = 0; i < d; i++) {
@@ -422,16 +452,17 @@ struct Solver {
             vec_dot(vi, r.get(), ld, slot[0], s);
             vec_sigma_scale(ui, mcols, slot[0], S.get() + i, s);
             prof.n_kernel_launches += 2;
+            LAS2_CUDA(cudaEventRecord(ev, s));
+            LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+            LAS2_CUDA(cudaMemcpyAsync(hU + i * mcols, ui, mcols * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
         }
-        const double td0 = wall();
-        LAS2_CUDA(cudaMemcpy2DAsync(hV, ncols * sizeof(double), V.get(), ld * sizeof(double), ncols * sizeof(double), d,
-                                    cudaMemcpyDeviceToHost, s));
-        LAS2_CUDA(cudaMemcpyAsync(hU, U.get(), d * mcols * sizeof(double), cudaMemcpyDeviceToHost, s));
         LAS2_CUDA(cudaMemcpyAsync(hS, S.get(), d * sizeof(double), cudaMemcpyDeviceToHost, s));
         LAS2_CUDA(cudaStreamSynchronize(s));
-        prof.n_host_syncs += 1;
+        const double td0 = wall();
+        LAS2_CUDA(cudaStreamSynchronize(copy_stream));
+        prof.n_host_syncs += 2;
         prof.d2h_bytes += (d * ncols + d * mcols + d) * sizeof(double);
-        prof.t_download = wall() - td0; // includes waiting for the tail kernels queued before the copies
+        prof.t_download = wall() - td0; // D2H time NOT hidden behind the sigma/U kernels
     }
 };
 
@@ -471,6 +502,12 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
     if (dimensions < 2)
         throw Error(SVDLAS2_ERR_LAS2, "svdLAS2: insufficient dimensions: " + std::to_string(dimensions)); // :596-600
 
+    cudaEvent_t ev_begin, ev_end;
+    LAS2_CUDA(cudaEventCreate(&ev_begin));
+    LAS2_CUDA(cudaEventCreate(&ev_end));
+    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev_guard{ev_begin, ev_end};
+    LAS2_CUDA(cudaEventRecord(ev_begin, op.stream));
+
     Solver sv(op, dimensions, iterations);
     u64 neig = 0;
     const double tl0 = wall();
@@ -501,6 +538,13 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
     sv.prof.t_ritvec = wall() - tr0;
     sv.prof.t_imtql2 = t_imtql2;
 
+    LAS2_CUDA(cudaEventRecord(ev_end, op.stream));
+    LAS2_CUDA(cudaEventSynchronize(ev_end));
+    {
+        float ms = 0.f;
+        LAS2_CUDA(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+        sv.prof.t_device = ms * 1e-3;
+    }
     if (op.profile) {
         double ms_total = 0.0;
         for (auto &e : sv.opb_events) {

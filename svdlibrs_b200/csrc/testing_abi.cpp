@@ -1,0 +1,61 @@
+// testing_abi.cpp -- include/svdlas2_testing.h: host-logic hooks for the CPU test-suite.
+#include "../../include/svdlas2_testing.h"
+
+#include <vector>
+
+#include "host_math.hpp"
+
+using namespace las2;
+
+extern "C" {
+
+void svdlas2_test_start_vector(uint32_t seed, uint64_t n, double *out) {
+    ChaCha12Stream g(seed);
+    for (uint64_t i = 0; i < n; i++) out[i] = g.next_unit_pm1();
+}
+
+double svdlas2_test_hypot(double a, double b) { return hypot_eispack(a, b); }
+
+int svdlas2_test_ql_values(uint64_t n, double *d, double *e, double *bnd) { return ql_values(n, d, e, bnd); }
+
+int svdlas2_test_ql_vectors(uint64_t n, double *d, double *e, double *z, uint64_t *n_rotations, uint64_t *n_sweeps) {
+    QlPlan plan;
+    int rc = ql_rotations(n, d, e, plan);
+    if (n_rotations) *n_rotations = plan.rotations();
+    if (n_sweeps) *n_sweeps = plan.sweeps.size();
+    if (rc) return rc;
+    // CPU replay, same arithmetic as k_ql_replay (tridiag_device.cu): zp holds the physical columns
+    std::vector<double> zp(n * n, 0.0);
+    for (uint64_t i = 0; i < n; i++) zp[i * n + i] = 1.0;
+    for (const QlSweep &sw : plan.sweeps) {
+        for (uint64_t row = 0; row < n; row++) {
+            double *zr = &zp[row * n];
+            uint32_t i = sw.hi;
+            double carry = zr[i + 1];
+            for (uint32_t t = 0; t < sw.count; t++, i--) {
+                const double s = plan.sc[2 * (sw.first + t)], c = plan.sc[2 * (sw.first + t) + 1];
+                const double x = zr[i];
+                zr[i + 1] = s * x + c * carry;
+                carry = c * x - s * carry;
+            }
+            zr[(uint32_t)(i + 1)] = carry;
+        }
+    }
+    for (uint64_t row = 0; row < n; row++)
+        for (uint64_t k = 0; k < n; k++) z[row * n + k] = zp[row * n + plan.column_of[k]];
+    return 0;
+}
+
+int svdlas2_test_refine_bounds(int *enough, double endl, double endr, double *ritz, double *bnd, uint64_t step,
+                               double tol, uint64_t *neig) {
+    bool en = *enough != 0;
+    size_t ne = 0;
+    int rc = refine_bounds(&en, endl, endr, ritz, bnd, step, tol, &ne);
+    *enough = en ? 1 : 0;
+    if (neig) *neig = ne;
+    return rc;
+}
+
+void svdlas2_test_cosort(uint64_t n, double *keys, double *vals) { cosort_ascending(n, keys, vals); }
+
+} // extern "C"
