@@ -15,10 +15,12 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--variant", type=int, default=-1)
 ap.add_argument("--flush", type=int, default=0)
+ap.add_argument("--hot", type=int, default=-1)
 a = ap.parse_args()
 A, dims = synthetic.make(a.workload, scale=a.scale)
 with las2.Operator(A) as op:
     op.set("spmv_variant", a.variant)
+    op.set("spmv_hot", a.hot)
     t = op.time_opb(reps=a.reps, flush_l2=bool(a.flush))
     t["GBs_opb"] = t["bytes_opb"] / t["ms_per_opb"] / 1e6
     t["GBs_b"] = t["bytes_spmv_b"] / t["ms_spmv_b"] / 1e6

@@ -7,6 +7,7 @@
 // entries and are therefore "effectively summed" exactly like src/lib.rs:2121-2127).
 #include "device_csr.cuh"
 
+#include <algorithm>
 #include <vector>
 
 namespace las2 {
@@ -295,6 +296,16 @@ __global__ void k_tile_rows(const u32 *__restrict__ off, u32 rows, u64 nnz, u32 
     tile_row[b] = lo;
 }
 
+// number of column indices below `limit` (integer count: order-independent)
+__global__ void k_count_below(const u32 *__restrict__ idx, u64 nnz, u32 limit, unsigned long long *__restrict__ out) {
+    u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    unsigned long long c = 0;
+    for (; k < nnz; k += stride) c += idx[k] < limit;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 inline u64 pad_to_tile(u64 nnz) { return ((nnz + kSpmvTile - 1) / kSpmvTile) * kSpmvTile + kSpmvTile; }
 
 void finish_csr(DeviceCsr &M, cudaStream_t s, UploadStats &st) {
@@ -312,6 +323,24 @@ void finish_csr(DeviceCsr &M, cudaStream_t s, UploadStats &st) {
     k_tile_rows<<<cdiv(M.num_tiles + 1, 256), 256, 0, s>>>(M.off, (u32)M.rows, M.nnz, M.num_tiles, M.tile_row);
     LAS2_LAUNCH_CHECK();
     st.launches++;
+    // is a shared-memory prefix of the gathered vector worth it for this matrix?
+    M.hot_entries = 0;
+    M.hot_fraction = 0.0;
+    if (M.nnz > 0) {
+        const u32 limit = (u32)std::min<u64>(kHotPrefix, M.cols);
+        DevBuf<unsigned long long> cnt(1);
+        LAS2_CUDA(cudaMemsetAsync(cnt.get(), 0, sizeof(unsigned long long), s));
+        unsigned grid = cdiv(M.nnz, 256 * 8);
+        if (grid > (unsigned)kNumSMs * 8) grid = kNumSMs * 8;
+        k_count_below<<<grid, 256, 0, s>>>(M.idx, M.nnz, limit, cnt);
+        LAS2_LAUNCH_CHECK();
+        st.launches++;
+        unsigned long long h = 0;
+        LAS2_CUDA(cudaMemcpyAsync(&h, cnt.get(), sizeof h, cudaMemcpyDeviceToHost, s));
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        M.hot_fraction = (double)h / (double)M.nnz;
+        if (M.hot_fraction >= 0.25) M.hot_entries = limit;
+    }
 }
 
 void check_err_flag(int *d_err, cudaStream_t s, const char *what) {

@@ -11,6 +11,8 @@ namespace las2 {
 
 // nnz-tile size of the streaming SpMV (see spmv.cu); value/index arrays are zero-padded to a multiple of it.
 constexpr u32 kSpmvTile = 2048;
+// candidate size of the shared-memory prefix of the gathered vector (64 KB of doubles)
+constexpr u32 kHotPrefix = 8192;
 
 struct DeviceCsr {
     u64 rows = 0, cols = 0, nnz = 0;
@@ -23,6 +25,10 @@ struct DeviceCsr {
     DevBuf<u32> tile_row;  // num_tiles + 1: first row that ENDS after the tile's first nnz (tile_row[0] = 0)
     DevBuf<double> carry;  // num_tiles: partial sum of the row that continues into the next tile
     DevBuf<double> head;   // num_tiles: partial sum of the tile's first row when it began in an earlier tile
+    // hot prefix of the gathered vector: entries [0, hot_entries) are worth keeping in shared memory when a
+    // large share of the column indices falls there (measured at upload: hot_fraction)
+    u32 hot_entries = 0;
+    double hot_fraction = 0.0;
     // algorithmic bytes of one y = A x with this matrix: 12*Z + 4*(R+1) + 8*C + 8*R
     u64 spmv_bytes() const { return 12 * nnz + 4 * (rows + 1) + 8 * cols + 8 * rows; }
 };

@@ -117,6 +117,123 @@ k_spmv_stream(const u32 *__restrict__ off, const u32 *__restrict__ idx, const do
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant with the hot prefix of the gathered vector in shared memory ("k_spmv_hot").
+//
+// Why: ncu on the first version (profiles/r1a_spmv_ncu_summary.md) shows DRAM at < 30 % with L1TEX at 84 %:
+// every gathered x[col] of a warp falls into its own 128-byte line and the L1TEX tag stage retires about one
+// line per cycle per SM, so an uncoalesced gather costs ~1 cycle per non-zero per SM no matter how fast HBM is.
+// Shared memory serves 32 random 8-byte reads in ~5 cycles.  So:
+//   * one CTA per SM (grid = 148), 4 groups of 256 threads; every group walks its own 2048-nnz tiles and
+//     synchronises on its own named barrier, so the groups of an SM sit in different phases (stream / reduce);
+//   * the first `hot` entries of x (the popular columns of an LSA-shaped matrix: term ids sorted by frequency)
+//     are copied to shared memory once per CTA; a gather with col < hot is an LDS, the rest go through L1TEX;
+//   * lanes take CONSECUTIVE non-zeros (scalar 8-byte / 4-byte streaming loads), so the 32 gathers of a warp
+//     instruction cover 32 adjacent entries of a row and dense regions coalesce into a few lines.
+constexpr int kHotGroups = 4;
+constexpr int kHotGroupThreads = 256;
+constexpr int kHotThreads = kHotGroups * kHotGroupThreads;
+constexpr int kHotRowChunk = 1024;
+
+struct HotGroupSmem {
+    double prod[kSpmvTile];
+    u32 roff[kHotRowChunk + 1];
+    u32 longq[kSpmvTile / kShortRow + 2];
+    u32 longn;
+};
+
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kHotGroupThreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kHotThreads, 1)
+k_spmv_hot(const u32 *__restrict__ off, const u32 *__restrict__ idx, const double *__restrict__ val,
+           const u32 *__restrict__ tile_row, const double *__restrict__ x, double *__restrict__ y,
+           double *__restrict__ carry, double *__restrict__ head, u32 rows, u32 nnz, u32 num_tiles, u32 hot) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HotGroupSmem *groups = reinterpret_cast<HotGroupSmem *>(smem_raw);
+    double *xs = reinterpret_cast<double *>(smem_raw + sizeof(HotGroupSmem) * kHotGroups);
+
+    const u64 pol_stream = l2_policy_evict_first();
+    const u64 pol_keep = l2_policy_evict_last();
+    for (u32 i = threadIdx.x; i < hot; i += kHotThreads) xs[i] = ld_gather_f64(x + i, pol_keep);
+    __syncthreads();
+
+    const int g = threadIdx.x / kHotGroupThreads;
+    const int tg = threadIdx.x % kHotGroupThreads;
+    const int lane = tg & 31, warp = tg >> 5;
+    constexpr int NW = kHotGroupThreads / 32;
+    constexpr int NPT = kSpmvTile / kHotGroupThreads;
+    HotGroupSmem &S = groups[g];
+
+    for (u32 tile = blockIdx.x * kHotGroups + g; tile < num_tiles; tile += gridDim.x * kHotGroups) {
+        const u32 start = tile * kSpmvTile;
+        const u32 end = min(start + kSpmvTile, nnz);
+        const u32 R0 = tile_row[tile];
+        const u32 R1 = tile_row[tile + 1];
+        // ---- stream + gather: lane-consecutive non-zeros ----
+        {
+            double v[NPT];
+            u32 c[NPT];
+#pragma unroll
+            for (int k = 0; k < NPT; k++) {
+                const u32 e = start + k * kHotGroupThreads + tg;
+                v[k] = ld_stream_f64(val + e, pol_stream);
+                c[k] = ld_stream_u32(idx + e, pol_stream);
+            }
+            double xv[NPT];
+#pragma unroll
+            for (int k = 0; k < NPT; k++) {
+                if (c[k] < hot) xv[k] = xs[c[k]];
+                else xv[k] = ld_gather_f64(x + c[k], pol_keep);
+            }
+#pragma unroll
+            for (int k = 0; k < NPT; k++) S.prod[k * kHotGroupThreads + tg] = v[k] * xv[k];
+        }
+        // ---- per-row reduction (same scheme as k_spmv_stream) ----
+        const u32 Rlast = (R1 < rows) ? R1 : rows - 1;
+        for (u32 rbase = R0; rbase <= Rlast; rbase += kHotRowChunk) {
+            const u32 nr = min((u32)kHotRowChunk, Rlast - rbase + 1);
+            for (u32 i = tg; i <= nr; i += kHotGroupThreads) S.roff[i] = off[rbase + i];
+            if (tg == 0) S.longn = 0;
+            group_sync(g);
+            for (u32 rr = tg; rr < nr; rr += kHotGroupThreads) {
+                const u32 r = rbase + rr;
+                const u32 o0 = S.roff[rr], o1 = S.roff[rr + 1];
+                const u32 lo = max(o0, start) - start;
+                const u32 hi = min(o1, end) - start;
+                if (hi > lo + kShortRow) {
+                    S.longq[atomicAdd(&S.longn, 1u)] = rr;
+                } else {
+                    double s = 0.0;
+                    for (u32 k = lo; k < hi; k++) s += S.prod[k];
+                    if (r == R1) carry[tile] = s;
+                    else if (o0 < start) head[tile] = s;
+                    else y[r] = s;
+                }
+            }
+            group_sync(g);
+            const u32 nlong = S.longn;
+            for (u32 qi = warp; qi < nlong; qi += NW) {
+                const u32 rr = S.longq[qi];
+                const u32 r = rbase + rr;
+                const u32 o0 = S.roff[rr], o1 = S.roff[rr + 1];
+                const u32 lo = max(o0, start) - start;
+                const u32 hi = min(o1, end) - start;
+                double s = 0.0;
+                for (u32 k = lo + lane; k < hi; k += 32) s += S.prod[k];
+                s = warp_sum(s);
+                if (lane == 0) {
+                    if (r == R1) carry[tile] = s;
+                    else if (o0 < start) head[tile] = s;
+                    else y[r] = s;
+                }
+            }
+            group_sync(g);
+        }
+    }
+}
+
 // Rows that straddle tile boundaries: y[r] = carry[b0] + ... + carry[b-1] + head[b], b = the tile the row ends in.
 __global__ void k_spmv_fixup(const u32 *__restrict__ off, const u32 *__restrict__ tile_row,
                              const double *__restrict__ carry, const double *__restrict__ head,
@@ -139,11 +256,35 @@ __global__ void k_spmv_fixup(const u32 *__restrict__ off, const u32 *__restrict_
 } // namespace
 
 int g_spmv_variant = -1;
+int g_spmv_hot_entries = -1; // -1 auto
+
+namespace {
+constexpr u32 kHotMaxEntries = 16384; // upper bound of the knob: 128 KB of the 227 KB
+size_t hot_smem_bytes(u32 hot) { return sizeof(HotGroupSmem) * kHotGroups + (size_t)hot * sizeof(double); }
+bool g_hot_attr_set = false;
+} // namespace
 
 void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
     if (A.rows == 0) return;
-    int variant = g_spmv_variant < 0 ? 0 : g_spmv_variant;
+    // variant: -1 auto, 0/1/2 = one CTA per tile with 256/128/512 threads, 3 = persistent hot-prefix kernel
+    int variant = g_spmv_variant;
+    if (variant < 0) variant = (A.num_tiles >= 8u * kNumSMs) ? 3 : 0;
     switch (variant) {
+    case 3: {
+        u32 hot = g_spmv_hot_entries >= 0 ? (u32)g_spmv_hot_entries : A.hot_entries;
+        if (hot > kHotMaxEntries) hot = kHotMaxEntries;
+        if (hot > A.cols) hot = (u32)A.cols;
+        if (!g_hot_attr_set) {
+            LAS2_CUDA(cudaFuncSetAttribute(k_spmv_hot, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)hot_smem_bytes(kHotMaxEntries)));
+            g_hot_attr_set = true;
+        }
+        u32 grid = kNumSMs;
+        if (grid * kHotGroups > A.num_tiles) grid = cdiv(A.num_tiles, kHotGroups);
+        k_spmv_hot<<<grid, kHotThreads, hot_smem_bytes(hot), s>>>(A.off, A.idx, A.val, A.tile_row, x, y, A.carry, A.head,
+                                                                 (u32)A.rows, (u32)A.nnz, A.num_tiles, hot);
+        break;
+    }
     case 1:
         k_spmv_stream<128><<<A.num_tiles, 128, 0, s>>>(A.off, A.idx, A.val, A.tile_row, x, y, A.carry, A.head,
                                                        (u32)A.rows, (u32)A.nnz);

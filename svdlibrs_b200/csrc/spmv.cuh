@@ -4,7 +4,8 @@
 
 namespace las2 {
 
-extern int g_spmv_variant; // -1 auto; test / tuning override (svdlas2_operator_set "spmv_variant")
+extern int g_spmv_variant;     // -1 auto; test / tuning override (svdlas2_operator_set "spmv_variant")
+extern int g_spmv_hot_entries; // -1 auto; entries of the gathered vector kept in shared memory ("spmv_hot")
 
 // y = A x on stream s.  x: A.cols doubles, y: A.rows doubles, both device-resident, no aliasing.
 void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches = nullptr);

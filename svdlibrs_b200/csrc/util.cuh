@@ -135,6 +135,11 @@ __device__ __forceinline__ uint4 ld_stream_u32x4(const u32 *p, u64 pol) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
     return r;
 }
+__device__ __forceinline__ u32 ld_stream_u32(const u32 *p, u64 pol) {
+    u32 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ double ld_stream_f64(const double *p, u64 pol) {
     double r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));

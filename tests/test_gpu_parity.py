@@ -213,3 +213,29 @@ def test_iterations_and_kappa_parameters(las2, oracle):
     ref = oracle.svd_las2(A, 10, 40, (-1e-30, 1e-30), 1e-4, 77)
     assert got.diagnostics.iterations == 40
     assert_svd_parity(got, ref)
+
+
+@pytest.mark.parametrize("variant,hot", [(0, -1), (1, -1), (2, -1), (3, 0), (3, 5), (3, 1000), (3, -1)])
+def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
+    """all SpMV kernels (one-CTA-per-tile with 256/128/512 threads, persistent hot-prefix kernel with several
+    shared-memory prefix sizes) on ragged + power-law inputs, both orientations"""
+    from svdlibrs_b200 import synthetic
+    rng = np.random.default_rng(21)
+    mats = [synthetic.make("cfg2", scale=0.01)[0],
+            sp.random(3000, 5000, density=0.004, format="csr", random_state=rng)]
+    lens = np.zeros(400, dtype=int); lens[3] = 6000; lens[4] = 1; lens[50:80] = 33; lens[100] = 2049; lens[399] = 7
+    rows = np.concatenate([np.full(l, i) for i, l in enumerate(lens)])
+    cols = np.concatenate([np.sort(rng.choice(7000, size=l, replace=False)) for l in lens])
+    mats.append(sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(400, 7000)))
+    for A in mats:
+        with las2.Operator(A) as op:
+            op.set("spmv_variant", variant)
+            op.set("spmv_hot", hot)
+            try:
+                for transposed in (False, True):
+                    x = rng.standard_normal(A.shape[0] if transposed else A.shape[1])
+                    y, y0 = op.opa(x, transposed), oracle.opa(A, x, transposed)
+                    assert np.linalg.norm(y - y0) <= 1e-13 * np.linalg.norm(y0)
+            finally:
+                op.set("spmv_variant", -1)
+                op.set("spmv_hot", -1)
