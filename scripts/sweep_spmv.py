@@ -13,7 +13,7 @@ a = ap.parse_args()
 A, dims = synthetic.make(a.workload, scale=a.scale)
 print(json.dumps(dict(workload=a.workload, shape=list(A.shape), nnz=int(A.nnz))))
 with las2.Operator(A) as op:
-    for variant, hot in [(3, -1), (3, 8192), (3, -1), (3, 0), (3, 4096), (3, 8192), (2, -1), (3, -1)]:
+    for variant, hot in [(4, -1), (3, -1), (2, -1), (4, -1)]:
         op.set("spmv_variant", variant); op.set("spmv_hot", hot)
         t = op.time_opb(reps=a.reps, flush_l2=False)
         print(json.dumps(dict(variant=variant, hot=hot, ms_opb=round(t["ms_per_opb"], 4), ms_b=round(t["ms_spmv_b"], 4),

@@ -282,11 +282,11 @@ __global__ void k_pad_tail(u32 *__restrict__ idx, double *__restrict__ val, u64 
 }
 
 // tile_row[b] = first row r with off[r+1] > b*kSpmvTile ; tile_row[0] = 0 ; tile_row[num_tiles] = rows
-__global__ void k_tile_rows(const u32 *__restrict__ off, u32 rows, u64 nnz, u32 num_tiles, u32 *__restrict__ tile_row) {
+__global__ void k_tile_rows(const u32 *__restrict__ off, u32 rows, u64 nnz, u32 num_tiles, u32 tile, u32 *__restrict__ tile_row) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > num_tiles) return;
     if (b == 0) { tile_row[0] = 0; return; }
-    u64 start = (u64)b * kSpmvTile;
+    u64 start = (u64)b * tile;
     if (b == num_tiles || start >= nnz) { tile_row[b] = rows; return; }
     u32 lo = 0, hi = rows;
     while (lo < hi) {
@@ -320,7 +320,7 @@ void finish_csr(DeviceCsr &M, cudaStream_t s, UploadStats &st) {
     M.tile_row.alloc(M.num_tiles + 1);
     M.carry.alloc(M.num_tiles);
     M.head.alloc(M.num_tiles);
-    k_tile_rows<<<cdiv(M.num_tiles + 1, 256), 256, 0, s>>>(M.off, (u32)M.rows, M.nnz, M.num_tiles, M.tile_row);
+    k_tile_rows<<<cdiv(M.num_tiles + 1, 256), 256, 0, s>>>(M.off, (u32)M.rows, M.nnz, M.num_tiles, kSpmvTile, M.tile_row);
     LAS2_LAUNCH_CHECK();
     st.launches++;
     // is a shared-memory prefix of the gathered vector worth it for this matrix?
@@ -410,6 +410,23 @@ void transpose_csr(const DeviceCsr &X, DeviceCsr &XT, cudaStream_t s, UploadStat
 
 } // namespace
 
+// helpers shared with blocked_csr.cu
+void exclusive_scan_u32(u32 *data, u64 n, cudaStream_t s, UploadStats &st) { exclusive_scan(data, n, s, st); }
+void expand_row_ids(const u32 *off, u32 rows, u64 nnz, u32 *rowid, cudaStream_t s, UploadStats &st) {
+    if (nnz == 0) return;
+    unsigned grid = cdiv(nnz, 256);
+    if (grid > (unsigned)kNumSMs * 32) grid = kNumSMs * 32;
+    k_expand_rows<<<grid, 256, 0, s>>>(off, rows, nnz, rowid);
+    LAS2_LAUNCH_CHECK();
+    st.launches++;
+}
+void build_tile_rows(const u32 *off, u32 rows, u64 nnz, u32 num_tiles, u32 tile, u32 *tile_row, cudaStream_t s, UploadStats &st) {
+    k_tile_rows<<<cdiv(num_tiles + 1, 256), 256, 0, s>>>(off, rows, nnz, num_tiles, tile, tile_row);
+    LAS2_LAUNCH_CHECK();
+    st.launches++;
+}
+void build_blocked(DeviceCsr &X, cudaStream_t s, UploadStats &st); // blocked_csr.cu
+
 void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, const u64 *indices, const double *values,
                              cudaStream_t s, DeviceCsr &X, DeviceCsr &XT, UploadStats &st) {
     if (nnz >= ((u64)1 << 32) - 2 * kSpmvTile || rows >= ((u64)1 << 32) - 1 || cols >= ((u64)1 << 32) - 1)
@@ -436,6 +453,8 @@ void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, co
     stage.release();
     finish_csr(X, s, st);
     transpose_csr(X, XT, s, st);
+    build_blocked(X, s, st);
+    build_blocked(XT, s, st);
 }
 
 void build_operator(const HostSparse &A, bool transposed, cudaStream_t s, DeviceCsr &B, DeviceCsr &BT, UploadStats &st) {
@@ -487,6 +506,8 @@ void build_operator(const HostSparse &A, bool transposed, cudaStream_t s, Device
         }
         finish_csr(X, s, st);
         transpose_csr(X, XT, s, st);
+        build_blocked(X, s, st);
+        build_blocked(XT, s, st);
     } else {
         throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "unknown sparse format");
     }

@@ -234,19 +234,260 @@ k_spmv_hot(const u32 *__restrict__ off, const u32 *__restrict__ idx, const doubl
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Column-blocked SpMV ("k_spmv_blocked"): every gather of a slab tile is served from shared memory, and the
+// non-zero stream arrives by TMA bulk copies (cp.async.bulk + mbarrier), not through registers.
+// Format: BlockedCsr (device_csr.cuh / blocked_csr.cu).  One CTA per SM, 4 groups of 256 threads.  Each CTA takes
+// a contiguous range of the slab tiles (so it needs the 128 KB slice of x of only one or two column blocks) and
+// an interleaved share of the remainder tiles (32-bit columns, gathered through L1/L2).  Per group and tile:
+//     wait(full)  ->  products = val * xs[idx]  into S.prod  ->  group barrier
+//     ->  thread 0 issues the bulk copy of the group's NEXT tile into the (now free) stage
+//     ->  per-row reduction of S.prod (the next tile streams in meanwhile)
+// Output: one partial per virtual row (slab, row); k_slab_reduce adds the slabs of a row in slab order.
+constexpr int kBlkGroups = 4;
+constexpr int kBlkGroupThreads = 256;
+constexpr int kBlkThreads = kBlkGroups * kBlkGroupThreads;
+constexpr int kBlkRowChunk = 1024;
+constexpr int kBlkRoffPerThread = (kBlkRowChunk + 1 + kBlkGroupThreads - 1) / kBlkGroupThreads; // 5
+
+struct __align__(128) BlkGroupSmem {
+    double sval[kBlkTile];             // TMA stage: values
+    u32 sidx[kBlkTile];                // TMA stage: u16 (slab tiles, first half used) or u32 (remainder) indices
+    double prod[kBlkTile];
+    u32 roff[kBlkRowChunk + 1];
+    u32 longq[kBlkTile / kShortRow + 2];
+    u32 longn;
+    unsigned long long full_bar;       // mbarrier: the stage has landed
+};
+
+__device__ __forceinline__ void blk_group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kBlkGroupThreads) : "memory");
+}
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 bytes, unsigned long long *bar, u64 pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n"
+                 " bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// per-row reduction of one tile whose products sit in S.prod.  `ro` holds the tile's first kBlkRowChunk+1 row
+// offsets, loaded by the caller before it waited for the stage (so their latency is already paid).
+// Balanced for any row-length mix: G = 1..32 lanes cooperate on a row, G chosen per tile from its mean row length
+// (so a tile of 30-entry rows uses 8 lanes per row instead of one thread or a whole warp); rows longer than
+// 32*G fall through to a warp-per-row pass.  All orders are fixed by the tile's structure: deterministic.
+__device__ __forceinline__ void blk_emit(double s, u32 r, u32 R1, u32 o0, u32 start, u32 tile, double *__restrict__ out,
+                                         double *__restrict__ carry, double *__restrict__ head) {
+    if (r == R1) carry[tile] = s;
+    else if (o0 < start) head[tile] = s;
+    else out[r] = s;
+}
+
+template <int G>
+__device__ __forceinline__ void blk_pass_a(BlkGroupSmem &S, int tg, u32 rbase, u32 nr, u32 start, u32 end, u32 tile,
+                                           u32 R1, double *__restrict__ out, double *__restrict__ carry,
+                                           double *__restrict__ head) {
+    const u32 sub = tg % G;
+    for (u32 rr0 = 0; rr0 < nr; rr0 += kBlkGroupThreads / G) {
+        const u32 rr = rr0 + tg / G;
+        const bool live = rr < nr;
+        u32 o0 = 0, lo = 0, hi = 0;
+        if (live) {
+            o0 = S.roff[rr];
+            const u32 o1 = S.roff[rr + 1];
+            lo = max(o0, start) - start;
+            hi = min(o1, end) - start;
+        }
+        const bool is_long = hi > lo + kShortRow * G;
+        double s = 0.0;
+        if (live && !is_long)
+            for (u32 k = lo + sub; k < hi; k += G) s += S.prod[k];
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (live && sub == 0) {
+            if (is_long) S.longq[atomicAdd(&S.longn, 1u)] = rr;
+            else blk_emit(s, rbase + rr, R1, o0, start, tile, out, carry, head);
+        }
+    }
+}
+
+__device__ __forceinline__ void blk_reduce_tile(BlkGroupSmem &S, int g, int tg, const u32 *__restrict__ voff,
+                                                u32 tile, u32 R0, u32 R1, u32 vrows, const u32 (&ro)[kBlkRoffPerThread],
+                                                double *__restrict__ out, double *__restrict__ carry,
+                                                double *__restrict__ head) {
+    const int lane = tg & 31, warp = tg >> 5;
+    constexpr int NW = kBlkGroupThreads / 32;
+    const u32 start = tile * kBlkTile, end = start + kBlkTile;
+    const u32 Rlast = (R1 < vrows) ? R1 : vrows - 1;
+    for (u32 rbase = R0; rbase <= Rlast; rbase += kBlkRowChunk) {
+        const u32 nr = min((u32)kBlkRowChunk, Rlast - rbase + 1);
+        if (rbase == R0) {
+#pragma unroll
+            for (int i = 0; i < kBlkRoffPerThread; i++) {
+                const u32 e = tg + i * kBlkGroupThreads;
+                if (e <= nr) S.roff[e] = ro[i];
+            }
+        } else {
+            for (u32 i = tg; i <= nr; i += kBlkGroupThreads) S.roff[i] = voff[rbase + i];
+        }
+        if (tg == 0) S.longn = 0;
+        blk_group_sync(g);
+        // lanes per row from the mean row length of this chunk (uniform over the group)
+        const u32 span = min(S.roff[nr], end) - max(S.roff[0], start);
+        const u32 mean = span / nr;
+        if (mean <= 6) blk_pass_a<1>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
+        else if (mean <= 12) blk_pass_a<2>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
+        else if (mean <= 24) blk_pass_a<4>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
+        else if (mean <= 48) blk_pass_a<8>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
+        else if (mean <= 96) blk_pass_a<16>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
+        else blk_pass_a<32>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
+        blk_group_sync(g);
+        const u32 nlong = S.longn;
+        for (u32 qi = warp; qi < nlong; qi += NW) {
+            const u32 rr = S.longq[qi];
+            const u32 o0 = S.roff[rr], o1 = S.roff[rr + 1];
+            const u32 lo = max(o0, start) - start;
+            const u32 hi = min(o1, end) - start;
+            double s = 0.0;
+            for (u32 k = lo + lane; k < hi; k += 32) s += S.prod[k];
+            s = warp_sum(s);
+            if (lane == 0) blk_emit(s, rbase + rr, R1, o0, start, tile, out, carry, head);
+        }
+        blk_group_sync(g);
+    }
+}
+
+// One group's walk over the tiles first, first+step, ... < stop.  SLAB: u16 local indices + shared-memory gathers;
+// otherwise u32 indices + global gathers.
+template <bool SLAB>
+__device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int tg, u32 &parity, u32 first, u32 stop, u32 step,
+                                         const u32 *__restrict__ voff, const uint16_t *__restrict__ idx16,
+                                         const u32 *__restrict__ idx32, u32 rem_tile0, const double *__restrict__ val,
+                                         const u32 *__restrict__ tile_row, const double *__restrict__ x,
+                                         const double *xs, double *__restrict__ out, double *__restrict__ carry,
+                                         double *__restrict__ head, u32 vrows, u64 pol_stream, u64 pol_keep) {
+    constexpr int NPT = kBlkTile / kBlkGroupThreads;
+    constexpr u32 kIdxBytes = SLAB ? kBlkTile * 2 : kBlkTile * 4;
+    auto issue = [&](u32 tile) {
+        mbar_expect_tx(&S.full_bar, kBlkTile * 8 + kIdxBytes);
+        tma_load_1d(S.sval, val + (u64)tile * kBlkTile, kBlkTile * 8, &S.full_bar, pol_stream);
+        if (SLAB) tma_load_1d(S.sidx, idx16 + (u64)tile * kBlkTile, kIdxBytes, &S.full_bar, pol_stream);
+        else tma_load_1d(S.sidx, idx32 + (u64)(tile - rem_tile0) * kBlkTile, kIdxBytes, &S.full_bar, pol_stream);
+    };
+    if (first >= stop) return;
+    if (tg == 0) issue(first);
+    for (u32 tile = first; tile < stop; tile += step) {
+        const u32 R0 = tile_row[tile], R1 = tile_row[tile + 1];
+        // row offsets of this tile: in flight while the stage lands
+        u32 ro[kBlkRoffPerThread];
+        {
+            const u32 Rlast = (R1 < vrows) ? R1 : vrows - 1;
+            const u32 nr = min((u32)kBlkRowChunk, Rlast - R0 + 1);
+#pragma unroll
+            for (int i = 0; i < kBlkRoffPerThread; i++) {
+                const u32 e = tg + i * kBlkGroupThreads;
+                ro[i] = (e <= nr) ? voff[R0 + e] : 0u;
+            }
+        }
+        mbar_wait(&S.full_bar, parity);
+        parity ^= 1u;
+        if (SLAB) {
+            const uint16_t *si = reinterpret_cast<const uint16_t *>(S.sidx);
+#pragma unroll
+            for (int k = 0; k < NPT; k++) {
+                const int e = k * kBlkGroupThreads + tg;
+                S.prod[e] = S.sval[e] * xs[si[e]];
+            }
+        } else {
+            double xv[NPT];
+#pragma unroll
+            for (int k = 0; k < NPT; k++) xv[k] = ld_gather_f64(x + S.sidx[k * kBlkGroupThreads + tg], pol_keep);
+#pragma unroll
+            for (int k = 0; k < NPT; k++) {
+                const int e = k * kBlkGroupThreads + tg;
+                S.prod[e] = S.sval[e] * xv[k];
+            }
+        }
+        blk_group_sync(g); // products complete, nobody reads the stage any more
+        if (tg == 0 && tile + step < stop) issue(tile + step);
+        blk_reduce_tile(S, g, tg, voff, tile, R0, R1, vrows, ro, out, carry, head);
+    }
+}
+
+__global__ void __launch_bounds__(kBlkThreads, 1)
+k_spmv_blocked(const u32 *__restrict__ voff, const uint16_t *__restrict__ idx16, const u32 *__restrict__ idx32,
+               const double *__restrict__ val, const u32 *__restrict__ tile_row, const u32 *__restrict__ slab_tile_start,
+               const double *__restrict__ x, double *__restrict__ out, double *__restrict__ carry,
+               double *__restrict__ head, u32 vrows, u32 cols, u32 nbk, u32 blocked_tiles, u32 num_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BlkGroupSmem *groups = reinterpret_cast<BlkGroupSmem *>(smem_raw);
+    double *xs = reinterpret_cast<double *>(smem_raw + sizeof(BlkGroupSmem) * kBlkGroups);
+
+    const u64 pol_stream = l2_policy_evict_first();
+    const u64 pol_keep = l2_policy_evict_last();
+    const int g = threadIdx.x / kBlkGroupThreads;
+    const int tg = threadIdx.x % kBlkGroupThreads;
+    BlkGroupSmem &S = groups[g];
+    if (tg == 0) {
+        mbar_init(&S.full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    u32 parity = 0;
+    __syncthreads();
+
+    // ---- slab tiles: contiguous share of [0, blocked_tiles) ----
+    const u32 t_begin = (u32)(((u64)blocked_tiles * blockIdx.x) / gridDim.x);
+    const u32 t_end = (u32)(((u64)blocked_tiles * (blockIdx.x + 1)) / gridDim.x);
+    u32 slab = 0;
+    for (u32 t = t_begin; t < t_end;) {
+        while (slab + 1 < nbk && slab_tile_start[slab + 1] <= t) slab++;
+        const u32 t_stop = min(t_end, slab_tile_start[slab + 1]);
+        __syncthreads(); // every group is done with the previous slice of x
+        const u32 c0 = slab * kBlockWidth;
+        for (u32 i = threadIdx.x; i < kBlockWidth; i += kBlkThreads)
+            xs[i] = (c0 + i < cols) ? ld_gather_f64(x + c0 + i, pol_keep) : 0.0;
+        __syncthreads();
+        blk_walk<true>(S, g, tg, parity, t + g, t_stop, kBlkGroups, voff, idx16, idx32, blocked_tiles, val, tile_row, x, xs,
+                       out, carry, head, vrows, pol_stream, pol_keep);
+        t = t_stop;
+    }
+    // ---- remainder tiles: interleaved share of [blocked_tiles, num_tiles), gathers through L1/L2 ----
+    blk_walk<false>(S, g, tg, parity, blocked_tiles + blockIdx.x * kBlkGroups + g, num_tiles, gridDim.x * kBlkGroups, voff,
+                    idx16, idx32, blocked_tiles, val, tile_row, x, xs, out, carry, head, vrows, pol_stream, pol_keep);
+}
+
+// y[r] = partial[0*R + r] + partial[1*R + r] + ... (slab order)
+__global__ void k_slab_reduce(const double *__restrict__ partial, u64 rows, u32 nslabs, double *__restrict__ y) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; r < rows; r += stride) {
+        double s = 0.0;
+        for (u32 b = 0; b < nslabs; b++) s += partial[(u64)b * rows + r];
+        y[r] = s;
+    }
+}
+
 // Rows that straddle tile boundaries: y[r] = carry[b0] + ... + carry[b-1] + head[b], b = the tile the row ends in.
 __global__ void k_spmv_fixup(const u32 *__restrict__ off, const u32 *__restrict__ tile_row,
                              const double *__restrict__ carry, const double *__restrict__ head,
-                             double *__restrict__ y, u32 num_tiles) {
+                             double *__restrict__ y, u32 num_tiles, u32 tile_nnz) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (b >= num_tiles) return;
     const u32 R0 = tile_row[b], R1 = tile_row[b + 1];
-    const u32 start = b * kSpmvTile;
+    const u32 start = b * tile_nnz;
     if (R0 < R1) {
         const u32 o0 = off[R0];
         if (o0 < start) {
             double s = 0.0;
-            for (u32 t = o0 / kSpmvTile; t < b; t++) s += carry[t];
+            for (u32 t = o0 / tile_nnz; t < b; t++) s += carry[t];
             s += head[b];
             y[R0] = s;
         }
@@ -264,8 +505,43 @@ size_t hot_smem_bytes(u32 hot) { return sizeof(HotGroupSmem) * kHotGroups + (siz
 bool g_hot_attr_set = false;
 } // namespace
 
+namespace {
+bool g_blk_attr_set = false;
+size_t blk_smem_bytes() { return sizeof(BlkGroupSmem) * kBlkGroups + (size_t)kBlockWidth * sizeof(double); }
+
+void spmv_blocked(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
+    const BlockedCsr &K = A.blk;
+    if (!g_blk_attr_set) {
+        LAS2_CUDA(cudaFuncSetAttribute(k_spmv_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_smem_bytes()));
+        g_blk_attr_set = true;
+    }
+    double *out = K.nslabs > 1 ? K.partial.get() : y;
+    u32 grid = kNumSMs;
+    if (grid * kBlkGroups > K.num_tiles) grid = cdiv(K.num_tiles, kBlkGroups);
+    k_spmv_blocked<<<grid, kBlkThreads, blk_smem_bytes(), s>>>(K.voff, K.idx16, K.idx32, K.val, K.tile_row,
+                                                              K.slab_tile_start, x, out, K.carry, K.head, (u32)K.vrows,
+                                                              (u32)K.cols, K.nbk, K.blocked_tiles, K.num_tiles);
+    if (K.num_tiles > 1) {
+        k_spmv_fixup<<<cdiv(K.num_tiles - 1, 128), 128, 0, s>>>(K.voff, K.tile_row, K.carry, K.head, out, K.num_tiles, kBlkTile);
+        if (launches) *launches += 1;
+    }
+    if (K.nslabs > 1) {
+        unsigned rg = cdiv(K.rows, 256);
+        if (rg > (unsigned)kNumSMs * 8) rg = kNumSMs * 8;
+        k_slab_reduce<<<rg, 256, 0, s>>>(K.partial, K.rows, K.nslabs, y);
+        if (launches) *launches += 1;
+    }
+    LAS2_LAUNCH_CHECK();
+    if (launches) *launches += 1;
+}
+} // namespace
+
 void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
     if (A.rows == 0) return;
+    if (A.blk.active && (g_spmv_variant < 0 || g_spmv_variant == 4)) {
+        spmv_blocked(A, x, y, s, launches);
+        return;
+    }
     // variant: -1 auto, 0/1/2 = one CTA per tile with 256/128/512 threads, 3 = persistent hot-prefix kernel
     int variant = g_spmv_variant;
     if (variant < 0) variant = (A.num_tiles >= 8u * kNumSMs) ? 3 : 0;
@@ -299,7 +575,7 @@ void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *l
         break;
     }
     if (A.num_tiles > 1) {
-        k_spmv_fixup<<<cdiv(A.num_tiles - 1, 128), 128, 0, s>>>(A.off, A.tile_row, A.carry, A.head, y, A.num_tiles);
+        k_spmv_fixup<<<cdiv(A.num_tiles - 1, 128), 128, 0, s>>>(A.off, A.tile_row, A.carry, A.head, y, A.num_tiles, kSpmvTile);
         if (launches) *launches += 1;
     }
     LAS2_LAUNCH_CHECK();

@@ -135,6 +135,11 @@ __device__ __forceinline__ uint4 ld_stream_u32x4(const u32 *p, u64 pol) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
     return r;
 }
+__device__ __forceinline__ u32 ld_stream_u16(const uint16_t *p, u64 pol) {
+    unsigned short r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(p), "l"(pol));
+    return (u32)r;
+}
 __device__ __forceinline__ u32 ld_stream_u32(const u32 *p, u64 pol) {
     u32 r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));

@@ -215,7 +215,7 @@ def test_iterations_and_kappa_parameters(las2, oracle):
     assert_svd_parity(got, ref)
 
 
-@pytest.mark.parametrize("variant,hot", [(0, -1), (1, -1), (2, -1), (3, 0), (3, 5), (3, 1000), (3, -1)])
+@pytest.mark.parametrize("variant,hot", [(0, -1), (1, -1), (2, -1), (3, 0), (3, 5), (3, 1000), (3, -1), (4, -1)])
 def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
     """all SpMV kernels (one-CTA-per-tile with 256/128/512 threads, persistent hot-prefix kernel with several
     shared-memory prefix sizes) on ragged + power-law inputs, both orientations"""
