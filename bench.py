@@ -306,7 +306,7 @@ def run_ours(args):
                       "accepted": res.diagnostics.singular_values, "sigma_max": float(res.s[0]) if res.d else None,
                       "purge_fired": int(res.profile["n_purge_fired"]), "purge_vectors": int(res.profile["n_purge_vectors"]),
                       "host_syncs": int(res.profile["n_host_syncs"]),
-                      "phases_s": {k: res.profile[k] for k in ("t_lanczos", "t_ritvec", "t_imtql2", "t_download")},
+                      "phases_s": {k: res.profile[k] for k in ("t_lanczos", "t_sync_wait", "t_ritvec", "t_imtql2", "t_download")},
                       "e2e_phases_s": {k: r2.profile[k] for k in ("t_upload", "t_lanczos", "t_ritvec", "t_download", "t_total")},
                       "e2e_equals_resident": bool(same)}}
 

@@ -82,6 +82,7 @@ typedef struct svdlas2_profile {
     double t_download;     /* D2H of ut / vt */
     double t_opb_device;   /* summed CUDA-event time of the opb SpMV pairs (0 unless profiling is on) */
     double t_device;       /* CUDA-event time on the operator's stream from solve entry to the last D2H */
+    double t_sync_wait;    /* host time blocked waiting for per-step scalars (inside t_lanczos) */
     uint64_t n_opb;        /* applications of B'(B x) */
     uint64_t n_spmv;       /* SpMV launches (2 per opb, +1 per returned vector) */
     uint64_t n_purge_fired;

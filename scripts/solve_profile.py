@@ -1,0 +1,18 @@
+"""One resident solve with the per-phase profile printed (no oracle).  python scripts/solve_profile.py [--workload cfg2] [--scale 1] [--reps 3]"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import svdlibrs_b200 as las2
+from svdlibrs_b200 import synthetic
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="cfg2"); ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--reps", type=int, default=3); ap.add_argument("--dims", type=int, default=0)
+a = ap.parse_args()
+A, dims = synthetic.make(a.workload, scale=a.scale)
+dims = a.dims or dims
+with las2.Operator(A) as op:
+    for i in range(a.reps):
+        t0 = time.perf_counter(); r = op.solve(dims, random_seed=12345); dt = time.perf_counter() - t0
+        p = r.profile
+        print(json.dumps(dict(wall=round(dt, 4), steps=r.diagnostics.lanczos_steps, d=r.d, n_opb=p["n_opb"],
+                              **{k: round(p[k], 4) for k in ("t_total", "t_lanczos", "t_sync_wait", "t_ritvec", "t_imtql2", "t_download", "t_device")},
+                              launches=p["n_kernel_launches"], syncs=p["n_host_syncs"], purge=p["n_purge_fired"])), flush=True)

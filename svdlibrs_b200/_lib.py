@@ -29,7 +29,7 @@ class Diagnostics(C.Structure):
 class Profile(C.Structure):
     _fields_ = [
         ("t_total", C.c_double), ("t_upload", C.c_double), ("t_lanczos", C.c_double), ("t_ritvec", C.c_double),
-        ("t_imtql2", C.c_double), ("t_download", C.c_double), ("t_opb_device", C.c_double), ("t_device", C.c_double),
+        ("t_imtql2", C.c_double), ("t_download", C.c_double), ("t_opb_device", C.c_double), ("t_device", C.c_double), ("t_sync_wait", C.c_double),
         ("n_opb", C.c_uint64), ("n_spmv", C.c_uint64), ("n_purge_fired", C.c_uint64),
         ("n_purge_passes", C.c_uint64), ("n_purge_vectors", C.c_uint64), ("n_restarts", C.c_uint64),
         ("n_kernel_launches", C.c_uint64), ("n_host_syncs", C.c_uint64),

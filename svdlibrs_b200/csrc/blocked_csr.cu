@@ -10,6 +10,7 @@
 //
 // Everything is built on the device and deterministically: integer counting, exclusive scan, ranked scatter.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "device_csr.cuh"
@@ -74,7 +75,10 @@ __global__ void k_blocked_scatter(const u32 *__restrict__ off, const u32 *__rest
             const u32 mid = lo + ((hi - lo) >> 1);
             if (idx[mid] < first_col) lo = mid + 1; else hi = mid;
         }
-        const u64 dest = (u64)voff[(u64)s * rows + r] + ((u32)k - lo);
+        const u64 logical = (u64)voff[(u64)s * rows + r] + ((u32)k - lo);
+        // interleaved tile layout: element j = t*8 + e of a tile lives at slot e*128 + t (see k_spmv_blocked)
+        const u64 j = logical % kBlkTile;
+        const u64 dest = logical - j + (j % 8) * (kBlkTile / 8) + j / 8;
         oval[dest] = val[k];
         if (s < nbk) idx16[dest] = (uint16_t)(c - first_col);
         else idx32[dest - rem_start] = c;
@@ -90,6 +94,10 @@ inline u64 round_up_tile(u64 v) { return (v + kBlkTile - 1) / kBlkTile * kBlkTil
 void build_blocked(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
     BlockedCsr &K = X.blk;
     K = BlockedCsr();
+    // Experimental (round 1): correct and parity-tested, but not yet faster than the plain-CSR kernels on B200
+    // (profiles/r1_spmv_iterations.md), so it is only built on request.
+    const char *want = std::getenv("SVDLAS2_BLOCKED");
+    if (!want || want[0] != '1') return;
     if (X.nnz == 0 || X.rows == 0) return;
     const u32 nblocks = cdiv(X.cols, kBlockWidth);
     if (nblocks > 12000) return; // shared histogram limit; such matrices are far too sparse per block anyway

@@ -134,7 +134,9 @@ struct Solver {
         for (int w : which) { g.parts[g.count] = slot[w].parts; g.nparts[g.count] = slot[w].nparts; g.count++; }
         gather_scalars(g, hs.get(), s);
         prof.n_kernel_launches += 1;
+        const double tw0 = wall();
         LAS2_CUDA(cudaStreamSynchronize(s));
+        prof.t_sync_wait += wall() - tw0;
         prof.n_host_syncs += 1;
         for (int i = 0; i < g.count; i++) out[i] = hs[i];
     }

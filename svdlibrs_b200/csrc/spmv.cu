@@ -235,33 +235,45 @@ k_spmv_hot(const u32 *__restrict__ off, const u32 *__restrict__ idx, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Column-blocked SpMV ("k_spmv_blocked"): every gather of a slab tile is served from shared memory, and the
-// non-zero stream arrives by TMA bulk copies (cp.async.bulk + mbarrier), not through registers.
-// Format: BlockedCsr (device_csr.cuh / blocked_csr.cu).  One CTA per SM, 4 groups of 256 threads.  Each CTA takes
-// a contiguous range of the slab tiles (so it needs the 128 KB slice of x of only one or two column blocks) and
-// an interleaved share of the remainder tiles (32-bit columns, gathered through L1/L2).  Per group and tile:
-//     wait(full)  ->  products = val * xs[idx]  into S.prod  ->  group barrier
-//     ->  thread 0 issues the bulk copy of the group's NEXT tile into the (now free) stage
-//     ->  per-row reduction of S.prod (the next tile streams in meanwhile)
+// Column-blocked SpMV ("k_spmv_blocked").  Format: BlockedCsr (device_csr.cuh / blocked_csr.cu).
+//
+// What ncu said about the earlier kernels (profiles/r1a..r1c): DRAM < 30 % busy while the L1TEX / shared-memory
+// data pipe ran at 58-84 % -- first from uncoalesced x[col] gathers (one 128-byte line per cycle per SM), then,
+// once the gathers came from shared memory, from parking every product in shared memory and re-reading it for
+// the per-row sums (0.77 wavefronts and ~70 thread instructions per non-zero).  This kernel therefore
+//   * gathers only from shared memory on slab tiles (the 128 KB slice of x of the slab's column block),
+//   * streams the non-zeros with TMA bulk copies (cp.async.bulk + mbarrier) into a per-group stage,
+//   * keeps the products in REGISTERS: inside a tile the stream is stored interleaved (element t*8+k at slot
+//     k*128+t), so the conflict-free read "slot k*128 + lane" hands every lane 8 CONSECUTIVE elements of the
+//     row-ordered stream; the lane sums them serially, cutting at the row starts (a 1024-bit map written by
+//     one thread per row), and a warp-shuffle segmented scan + a 4-entry cross-warp step stitch the rows that
+//     span lanes.  No product ever touches shared memory; every order is fixed by the tile: deterministic.
+// One CTA per SM, 5 groups of 128 threads, each with its own stage / mbarrier / named barrier, walking its own
+// tiles.  Each CTA takes a contiguous range of the slab tiles (one or two column blocks -> one or two loads of
+// the x slice) and an interleaved share of the remainder tiles (32-bit columns, gathered through L1/L2).
 // Output: one partial per virtual row (slab, row); k_slab_reduce adds the slabs of a row in slab order.
-constexpr int kBlkGroups = 4;
-constexpr int kBlkGroupThreads = 256;
-constexpr int kBlkThreads = kBlkGroups * kBlkGroupThreads;
-constexpr int kBlkRowChunk = 1024;
-constexpr int kBlkRoffPerThread = (kBlkRowChunk + 1 + kBlkGroupThreads - 1) / kBlkGroupThreads; // 5
+constexpr int kBlkGroups = 5;
+constexpr int kBlkLanes = 128; // threads per group
+constexpr int kBlkE = kBlkTile / kBlkLanes; // 8 consecutive elements per lane
+constexpr int kBlkThreads = kBlkGroups * kBlkLanes;
+constexpr int kBlkWarps = kBlkLanes / 32;
+constexpr int kBlkRowChunk = 256;
+constexpr int kBlkRoffPerThread = (kBlkRowChunk + 1 + kBlkLanes - 1) / kBlkLanes; // 3
+static_assert(kBlkE == 8, "the flag byte per lane assumes 8 elements per lane");
 
 struct __align__(128) BlkGroupSmem {
-    double sval[kBlkTile];             // TMA stage: values
-    u32 sidx[kBlkTile];                // TMA stage: u16 (slab tiles, first half used) or u32 (remainder) indices
-    double prod[kBlkTile];
+    double sval[kBlkTile];        // TMA stage: values (interleaved order)
+    u32 sidx[kBlkTile];           // TMA stage: u16 (slab tiles, first half used) or u32 (remainder) indices
+    u32 rowat[kBlkTile];          // virtual row whose piece starts at this element (valid where the flag is set)
     u32 roff[kBlkRowChunk + 1];
-    u32 longq[kBlkTile / kShortRow + 2];
-    u32 longn;
-    unsigned long long full_bar;       // mbarrier: the stage has landed
+    u32 flags[kBlkTile / 32];     // bit e: a row piece starts at element e
+    double wsum[kBlkWarps];       // warp aggregates of the segmented scan
+    u32 wfr[kBlkWarps];
+    unsigned long long full_bar;  // mbarrier: the stage has landed
 };
 
 __device__ __forceinline__ void blk_group_sync(int g) {
-    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kBlkGroupThreads) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kBlkLanes) : "memory");
 }
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count) {
@@ -279,103 +291,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity) {
                  " bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-// per-row reduction of one tile whose products sit in S.prod.  `ro` holds the tile's first kBlkRowChunk+1 row
-// offsets, loaded by the caller before it waited for the stage (so their latency is already paid).
-// Balanced for any row-length mix: G = 1..32 lanes cooperate on a row, G chosen per tile from its mean row length
-// (so a tile of 30-entry rows uses 8 lanes per row instead of one thread or a whole warp); rows longer than
-// 32*G fall through to a warp-per-row pass.  All orders are fixed by the tile's structure: deterministic.
-__device__ __forceinline__ void blk_emit(double s, u32 r, u32 R1, u32 o0, u32 start, u32 tile, double *__restrict__ out,
-                                         double *__restrict__ carry, double *__restrict__ head) {
-    if (r == R1) carry[tile] = s;
-    else if (o0 < start) head[tile] = s;
-    else out[r] = s;
-}
-
-template <int G>
-__device__ __forceinline__ void blk_pass_a(BlkGroupSmem &S, int tg, u32 rbase, u32 nr, u32 start, u32 end, u32 tile,
-                                           u32 R1, double *__restrict__ out, double *__restrict__ carry,
-                                           double *__restrict__ head) {
-    const u32 sub = tg % G;
-    for (u32 rr0 = 0; rr0 < nr; rr0 += kBlkGroupThreads / G) {
-        const u32 rr = rr0 + tg / G;
-        const bool live = rr < nr;
-        u32 o0 = 0, lo = 0, hi = 0;
-        if (live) {
-            o0 = S.roff[rr];
-            const u32 o1 = S.roff[rr + 1];
-            lo = max(o0, start) - start;
-            hi = min(o1, end) - start;
-        }
-        const bool is_long = hi > lo + kShortRow * G;
-        double s = 0.0;
-        if (live && !is_long)
-            for (u32 k = lo + sub; k < hi; k += G) s += S.prod[k];
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (live && sub == 0) {
-            if (is_long) S.longq[atomicAdd(&S.longn, 1u)] = rr;
-            else blk_emit(s, rbase + rr, R1, o0, start, tile, out, carry, head);
-        }
-    }
-}
-
-__device__ __forceinline__ void blk_reduce_tile(BlkGroupSmem &S, int g, int tg, const u32 *__restrict__ voff,
-                                                u32 tile, u32 R0, u32 R1, u32 vrows, const u32 (&ro)[kBlkRoffPerThread],
-                                                double *__restrict__ out, double *__restrict__ carry,
-                                                double *__restrict__ head) {
-    const int lane = tg & 31, warp = tg >> 5;
-    constexpr int NW = kBlkGroupThreads / 32;
-    const u32 start = tile * kBlkTile, end = start + kBlkTile;
-    const u32 Rlast = (R1 < vrows) ? R1 : vrows - 1;
-    for (u32 rbase = R0; rbase <= Rlast; rbase += kBlkRowChunk) {
-        const u32 nr = min((u32)kBlkRowChunk, Rlast - rbase + 1);
-        if (rbase == R0) {
-#pragma unroll
-            for (int i = 0; i < kBlkRoffPerThread; i++) {
-                const u32 e = tg + i * kBlkGroupThreads;
-                if (e <= nr) S.roff[e] = ro[i];
-            }
-        } else {
-            for (u32 i = tg; i <= nr; i += kBlkGroupThreads) S.roff[i] = voff[rbase + i];
-        }
-        if (tg == 0) S.longn = 0;
-        blk_group_sync(g);
-        // lanes per row from the mean row length of this chunk (uniform over the group)
-        const u32 span = min(S.roff[nr], end) - max(S.roff[0], start);
-        const u32 mean = span / nr;
-        if (mean <= 6) blk_pass_a<1>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
-        else if (mean <= 12) blk_pass_a<2>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
-        else if (mean <= 24) blk_pass_a<4>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
-        else if (mean <= 48) blk_pass_a<8>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
-        else if (mean <= 96) blk_pass_a<16>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
-        else blk_pass_a<32>(S, tg, rbase, nr, start, end, tile, R1, out, carry, head);
-        blk_group_sync(g);
-        const u32 nlong = S.longn;
-        for (u32 qi = warp; qi < nlong; qi += NW) {
-            const u32 rr = S.longq[qi];
-            const u32 o0 = S.roff[rr], o1 = S.roff[rr + 1];
-            const u32 lo = max(o0, start) - start;
-            const u32 hi = min(o1, end) - start;
-            double s = 0.0;
-            for (u32 k = lo + lane; k < hi; k += 32) s += S.prod[k];
-            s = warp_sum(s);
-            if (lane == 0) blk_emit(s, rbase + rr, R1, o0, start, tile, out, carry, head);
-        }
-        blk_group_sync(g);
-    }
-}
+constexpr u32 kSegFlag = 0x80000000u; // scan element: (sum, fr) with fr = kSegFlag | row when a piece starts in it
 
 // One group's walk over the tiles first, first+step, ... < stop.  SLAB: u16 local indices + shared-memory gathers;
 // otherwise u32 indices + global gathers.
 template <bool SLAB>
-__device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int tg, u32 &parity, u32 first, u32 stop, u32 step,
+__device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int t, u32 &parity, u32 first, u32 stop, u32 step,
                                          const u32 *__restrict__ voff, const uint16_t *__restrict__ idx16,
                                          const u32 *__restrict__ idx32, u32 rem_tile0, const double *__restrict__ val,
                                          const u32 *__restrict__ tile_row, const double *__restrict__ x,
                                          const double *xs, double *__restrict__ out, double *__restrict__ carry,
                                          double *__restrict__ head, u32 vrows, u64 pol_stream, u64 pol_keep) {
-    constexpr int NPT = kBlkTile / kBlkGroupThreads;
     constexpr u32 kIdxBytes = SLAB ? kBlkTile * 2 : kBlkTile * 4;
+    const int lane = t & 31, warp = t >> 5;
     auto issue = [&](u32 tile) {
         mbar_expect_tx(&S.full_bar, kBlkTile * 8 + kIdxBytes);
         tma_load_1d(S.sval, val + (u64)tile * kBlkTile, kBlkTile * 8, &S.full_bar, pol_stream);
@@ -383,42 +311,127 @@ __device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int tg, u32 &pa
         else tma_load_1d(S.sidx, idx32 + (u64)(tile - rem_tile0) * kBlkTile, kIdxBytes, &S.full_bar, pol_stream);
     };
     if (first >= stop) return;
-    if (tg == 0) issue(first);
+    if (t == 0) issue(first);
     for (u32 tile = first; tile < stop; tile += step) {
+        const u32 start = tile * kBlkTile, end = start + kBlkTile;
         const u32 R0 = tile_row[tile], R1 = tile_row[tile + 1];
-        // row offsets of this tile: in flight while the stage lands
+        const u32 Rlast = (R1 < vrows) ? R1 : vrows - 1;
+        // row offsets of the first row chunk: in flight while the stage lands
         u32 ro[kBlkRoffPerThread];
-        {
-            const u32 Rlast = (R1 < vrows) ? R1 : vrows - 1;
-            const u32 nr = min((u32)kBlkRowChunk, Rlast - R0 + 1);
+        const u32 nr0 = min((u32)kBlkRowChunk, Rlast - R0 + 1);
 #pragma unroll
-            for (int i = 0; i < kBlkRoffPerThread; i++) {
-                const u32 e = tg + i * kBlkGroupThreads;
-                ro[i] = (e <= nr) ? voff[R0 + e] : 0u;
-            }
+        for (int i = 0; i < kBlkRoffPerThread; i++) {
+            const u32 e = t + i * kBlkLanes;
+            ro[i] = (e <= nr0) ? voff[R0 + e] : 0u;
         }
         mbar_wait(&S.full_bar, parity);
         parity ^= 1u;
+        // ---- stage -> registers: slot k*128 + t holds element t*8 + k ----
+        double p[kBlkE];
+        u32 c[kBlkE];
+#pragma unroll
+        for (int k = 0; k < kBlkE; k++) {
+            p[k] = S.sval[k * kBlkLanes + t];
+            c[k] = SLAB ? (u32) reinterpret_cast<const uint16_t *>(S.sidx)[k * kBlkLanes + t] : S.sidx[k * kBlkLanes + t];
+        }
+        if (t < kBlkTile / 32) S.flags[t] = 0;
+#pragma unroll
+        for (int i = 0; i < kBlkRoffPerThread; i++) {
+            const u32 e = t + i * kBlkLanes;
+            if (e <= nr0) S.roff[e] = ro[i];
+        }
+        blk_group_sync(g); // stage consumed, flags cleared, first row chunk staged
+        if (t == 0 && tile + step < stop) issue(tile + step);
+        // ---- gathers + products (registers only) ----
         if (SLAB) {
-            const uint16_t *si = reinterpret_cast<const uint16_t *>(S.sidx);
 #pragma unroll
-            for (int k = 0; k < NPT; k++) {
-                const int e = k * kBlkGroupThreads + tg;
-                S.prod[e] = S.sval[e] * xs[si[e]];
-            }
+            for (int k = 0; k < kBlkE; k++) p[k] *= xs[c[k]];
         } else {
-            double xv[NPT];
+            double xv[kBlkE];
 #pragma unroll
-            for (int k = 0; k < NPT; k++) xv[k] = ld_gather_f64(x + S.sidx[k * kBlkGroupThreads + tg], pol_keep);
+            for (int k = 0; k < kBlkE; k++) xv[k] = ld_gather_f64(x + c[k], pol_keep);
 #pragma unroll
-            for (int k = 0; k < NPT; k++) {
-                const int e = k * kBlkGroupThreads + tg;
-                S.prod[e] = S.sval[e] * xv[k];
+            for (int k = 0; k < kBlkE; k++) p[k] *= xv[k];
+        }
+        // ---- one thread per row: mark where its piece starts; rows with no entry in this tile are zero ----
+        const bool first_is_head = S.roff[0] < start; // row R0 began in an earlier tile
+        auto emit = [&](u32 r, double v) {
+            if (r == R1) carry[tile] = v;
+            else if (r == R0 && first_is_head) head[tile] = v;
+            else out[r] = v;
+        };
+        for (u32 rbase = R0; rbase <= Rlast; rbase += kBlkRowChunk) {
+            const u32 nr = min((u32)kBlkRowChunk, Rlast - rbase + 1);
+            if (rbase != R0) {
+                blk_group_sync(g); // everyone is done with the previous chunk's offsets
+                for (u32 i = t; i <= nr; i += kBlkLanes) S.roff[i] = voff[rbase + i];
+                blk_group_sync(g);
+            }
+            for (u32 rr = t; rr < nr; rr += kBlkLanes) {
+                const u32 r = rbase + rr;
+                const u32 o0 = S.roff[rr], o1 = S.roff[rr + 1];
+                const u32 lo = max(o0, start) - start;
+                const u32 hi = min(o1, end) - start;
+                if (hi > lo) {
+                    atomicOr(&S.flags[lo >> 5], 1u << (lo & 31)); // integer bit set: order-independent
+                    S.rowat[lo] = r;
+                } else {
+                    emit(r, 0.0);
+                }
             }
         }
-        blk_group_sync(g); // products complete, nobody reads the stage any more
-        if (tg == 0 && tile + step < stop) issue(tile + step);
-        blk_reduce_tile(S, g, tg, voff, tile, R0, R1, vrows, ro, out, carry, head);
+        blk_group_sync(g); // flags and rowat complete
+        // ---- per-lane serial segmented sum over its 8 consecutive elements ----
+        const u32 fl = (S.flags[t >> 2] >> ((t & 3) * 8)) & 0xffu;
+        double s = 0.0, head_sum = 0.0;
+        bool open_here = false;
+        u32 open_row = 0;
+#pragma unroll
+        for (int k = 0; k < kBlkE; k++) {
+            if ((fl >> k) & 1u) {
+                if (open_here) emit(open_row, s);
+                else head_sum = s;
+                s = 0.0;
+                open_here = true;
+                open_row = S.rowat[t * kBlkE + k];
+            }
+            s += p[k];
+        }
+        // ---- stitch pieces that span lanes: warp segmented scan, then the 4 warp aggregates ----
+        double xsum = s;
+        u32 fr = open_here ? (kSegFlag | open_row) : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double ys = __shfl_up_sync(0xffffffffu, xsum, o);
+            const u32 yf = __shfl_up_sync(0xffffffffu, fr, o);
+            if (lane >= o && !(fr & kSegFlag)) { xsum = ys + xsum; fr = yf; }
+        }
+        if (lane == 31) { S.wsum[warp] = xsum; S.wfr[warp] = fr; }
+        // exclusive value inside the warp
+        double cin_sum = __shfl_up_sync(0xffffffffu, xsum, 1);
+        u32 cin_fr = __shfl_up_sync(0xffffffffu, fr, 1);
+        if (lane == 0) { cin_sum = 0.0; cin_fr = 0u; }
+        blk_group_sync(g);
+        // fold the aggregates of the warps to the left (in order) in front of it
+        double acc_sum = 0.0;
+        u32 acc_fr = 0u;
+        for (int w = 0; w < warp; w++) {
+            const double ws = S.wsum[w];
+            const u32 wf = S.wfr[w];
+            if (wf & kSegFlag) { acc_sum = ws; acc_fr = wf; }
+            else acc_sum = acc_sum + ws;
+        }
+        if (!(cin_fr & kSegFlag)) { cin_sum = acc_sum + cin_sum; cin_fr = acc_fr; }
+        // a lane that starts a piece closes the piece that was open when it began
+        if (open_here) {
+            if (cin_fr & kSegFlag) emit(cin_fr & ~kSegFlag, cin_sum + head_sum);
+        }
+        // the piece still open at the end of the tile
+        if (t == kBlkLanes - 1) {
+            if (open_here) emit(open_row, s);
+            else if (cin_fr & kSegFlag) emit(cin_fr & ~kSegFlag, cin_sum + s);
+        }
+        // (the next tile's first barrier separates these reads of wsum / rowat / flags from their next writes)
     }
 }
 
@@ -433,10 +446,10 @@ k_spmv_blocked(const u32 *__restrict__ voff, const uint16_t *__restrict__ idx16,
 
     const u64 pol_stream = l2_policy_evict_first();
     const u64 pol_keep = l2_policy_evict_last();
-    const int g = threadIdx.x / kBlkGroupThreads;
-    const int tg = threadIdx.x % kBlkGroupThreads;
+    const int g = threadIdx.x / kBlkLanes;
+    const int t = threadIdx.x % kBlkLanes;
     BlkGroupSmem &S = groups[g];
-    if (tg == 0) {
+    if (t == 0) {
         mbar_init(&S.full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -447,20 +460,20 @@ k_spmv_blocked(const u32 *__restrict__ voff, const uint16_t *__restrict__ idx16,
     const u32 t_begin = (u32)(((u64)blocked_tiles * blockIdx.x) / gridDim.x);
     const u32 t_end = (u32)(((u64)blocked_tiles * (blockIdx.x + 1)) / gridDim.x);
     u32 slab = 0;
-    for (u32 t = t_begin; t < t_end;) {
-        while (slab + 1 < nbk && slab_tile_start[slab + 1] <= t) slab++;
+    for (u32 tt = t_begin; tt < t_end;) {
+        while (slab + 1 < nbk && slab_tile_start[slab + 1] <= tt) slab++;
         const u32 t_stop = min(t_end, slab_tile_start[slab + 1]);
         __syncthreads(); // every group is done with the previous slice of x
         const u32 c0 = slab * kBlockWidth;
         for (u32 i = threadIdx.x; i < kBlockWidth; i += kBlkThreads)
             xs[i] = (c0 + i < cols) ? ld_gather_f64(x + c0 + i, pol_keep) : 0.0;
         __syncthreads();
-        blk_walk<true>(S, g, tg, parity, t + g, t_stop, kBlkGroups, voff, idx16, idx32, blocked_tiles, val, tile_row, x, xs,
+        blk_walk<true>(S, g, t, parity, tt + g, t_stop, kBlkGroups, voff, idx16, idx32, blocked_tiles, val, tile_row, x, xs,
                        out, carry, head, vrows, pol_stream, pol_keep);
-        t = t_stop;
+        tt = t_stop;
     }
     // ---- remainder tiles: interleaved share of [blocked_tiles, num_tiles), gathers through L1/L2 ----
-    blk_walk<false>(S, g, tg, parity, blocked_tiles + blockIdx.x * kBlkGroups + g, num_tiles, gridDim.x * kBlkGroups, voff,
+    blk_walk<false>(S, g, t, parity, blocked_tiles + blockIdx.x * kBlkGroups + g, num_tiles, gridDim.x * kBlkGroups, voff,
                     idx16, idx32, blocked_tiles, val, tile_row, x, xs, out, carry, head, vrows, pol_stream, pol_keep);
 }
 

@@ -219,7 +219,9 @@ def test_iterations_and_kappa_parameters(las2, oracle):
 def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
     """all SpMV kernels (one-CTA-per-tile with 256/128/512 threads, persistent hot-prefix kernel with several
     shared-memory prefix sizes) on ragged + power-law inputs, both orientations"""
+    import os
     from svdlibrs_b200 import synthetic
+    os.environ["SVDLAS2_BLOCKED"] = "1" if variant == 4 else "0"   # the column-blocked copy is built on request
     rng = np.random.default_rng(21)
     mats = [synthetic.make("cfg2", scale=0.01)[0],
             sp.random(3000, 5000, density=0.004, format="csr", random_state=rng)]
@@ -239,3 +241,4 @@ def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
             finally:
                 op.set("spmv_variant", -1)
                 op.set("spmv_hot", -1)
+                os.environ["SVDLAS2_BLOCKED"] = "0"
