@@ -73,7 +73,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self) -> dict:
+    def mark(self) -> int:
+        """index of the next sample: brackets the timed region (the sampler itself starts before the warm-up so
+        that spawning nvidia-smi, which briefly blocks CUDA calls, stays out of the timed steps)"""
+        return len(self.rows)
+
+    def stop(self, first: int = 0, last: int | None = None) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -83,7 +88,8 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[first:(last if last is not None and last > first else None)] or self.rows
+        for r in rows:
             if len(r) < 9:
                 continue
             try:
@@ -164,10 +170,15 @@ def pinned_like(a: np.ndarray, torch):
 
 
 def run_ours(args):
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries the one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: svdlibrs_b200 has no CPU fallback")
     torch.cuda.set_device(local)
@@ -218,11 +229,10 @@ def run_ours(args):
         hv, _k3 = pinned_like(Bl.data.astype(np.float64), torch)
         Bl_pinned = las2.RawMatrix("csr", Bl.shape, hp, hi, hv)
         h2d_step = hp.nbytes + hi.nbytes + hv.nbytes
-        comm_id = sharding.broadcast_comm_id(dist, rank)
+        comm = las2.Communicator(rank, world, sharding.broadcast_comm_id(dist, rank), device=local)
 
         def make_resident():
-            return las2.ShardedOperator(Bl_pinned, B.shape[0], lo, int(B.nnz), rank, world, comm_id, transposed,
-                                        device=local)
+            return las2.ShardedOperator(Bl_pinned, B.shape[0], lo, int(B.nnz), comm, transposed, device=local)
 
         def e2e_call():
             with make_resident() as op_:
@@ -231,28 +241,38 @@ def run_ours(args):
     # ---------------- resident leg: value
     op = make_resident()
     sampler = ClockSampler(local)
-    res = None
-    for _ in range(args.warmup):
-        res = op.solve(dims, 0, endi, kappa, SEED)
-    barrier()
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    res = None
+    for _ in range(args.warmup):
+        res = None
+        res = op.solve(dims, 0, endi, kappa, SEED)
+    barrier()
+    mark0 = sampler.mark()
     t_dev, launches, wall0 = 0.0, 0, time.perf_counter()
     for _ in range(args.steps):
+        res = None  # hand the previous result's pinned buffers back to the library's pool before the next call
         res = op.solve(dims, 0, endi, kappa, SEED)
         t_dev += res.profile["t_device"]
         launches += res.profile["n_kernel_launches"]
+        if rank == 0:
+            log("[resident] " + json.dumps({k: round(res.profile[k], 4) for k in
+                                            ("t_total", "t_lanczos", "t_ritvec", "t_imtql2", "t_device")}))
     barrier()
     wall_resident = time.perf_counter() - wall0
     t_dev = max_over_ranks(t_dev)
-    n_opb = res.profile["n_opb"]
+    # numerator: the opb applications the REFERENCE algorithm performs for this solve (one per Lanczos
+    # step, one in startv, one per restart, one per returned triplet) -- the same for both arms because step counts
+    # are identical; the library itself needs fewer (sigma = |B v| saves the tail's second SpMV), see solve.n_opb_run
+    n_opb = res.diagnostics.lanczos_steps + 1 + res.d + int(res.profile["n_restarts"])
     value = n_opb * args.steps / t_dev
 
     # ---------------- roofline leg: the dominant kernel, timed live with CUDA events on the library's stream
     flush = 24 * A.nnz <= 4 * 126e6
     tm = op.time_opb(reps=20, flush_l2=flush)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark0, sampler.mark() + 1) if rank == 0 else None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (burst copy)"
@@ -281,8 +301,12 @@ def run_ours(args):
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
+        r2 = None
         r2 = e2e_call()
         d2h = r2.profile["d2h_bytes"]
+        if rank == 0:
+            log("[e2e] " + json.dumps({k: round(r2.profile[k], 4) for k in
+                                       ("t_total", "t_upload", "t_lanczos", "t_ritvec", "t_imtql2", "t_device")}))
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_opb * args.steps / t_e2e
@@ -301,7 +325,8 @@ def run_ours(args):
             "time_to_svd_s": {"resident": t_dev / args.steps, "resident_wall": wall_resident / args.steps,
                               "e2e": t_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "solve": {"lanczos_steps": res.diagnostics.lanczos_steps, "n_opb": int(n_opb),
+            "solve": {"lanczos_steps": res.diagnostics.lanczos_steps, "n_opb": int(n_opb), "n_opb_run": int(res.profile["n_opb"]),
+                      "n_spmv_run": int(res.profile["n_spmv"]),
                       "ritz_values_stabilized": res.diagnostics.ritz_values_stabilized, "d": res.d,
                       "accepted": res.diagnostics.singular_values, "sigma_max": float(res.s[0]) if res.d else None,
                       "purge_fired": int(res.profile["n_purge_fired"]), "purge_vectors": int(res.profile["n_purge_vectors"]),
@@ -320,6 +345,8 @@ def run_ours(args):
                                 "host_cpus": os.cpu_count()}
     else:
         line["cpu_baseline"] = None
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -178,19 +178,24 @@ SVDLAS2_API int svdlas2_operator_set(svdlas2_operator *op, const char *knob, int
 
 #define SVDLAS2_COMM_ID_BYTES 128
 /* rank 0 fills an opaque id, the caller broadcasts it (torch.distributed / MPI / a file), then every rank
- * creates its shard with the same id. */
+ * creates its communicator with the same id.  A communicator is long-lived and serves any number of shards. */
 SVDLAS2_API int svdlas2_comm_unique_id(uint8_t id[SVDLAS2_COMM_ID_BYTES]);
+
+typedef struct svdlas2_comm svdlas2_comm;
+SVDLAS2_API int svdlas2_comm_create(int rank, int world_size, const uint8_t id[SVDLAS2_COMM_ID_BYTES], int device,
+                        svdlas2_comm **comm);
+SVDLAS2_API void svdlas2_comm_destroy(svdlas2_comm *comm);
 
 /* Row shard [row_begin, row_end) of B in CSR form: local_offsets has (row_end-row_begin)+1 entries starting
  * at 0, local_indices are column indices < n.  m_global/n are B's full shape.  `b_is_a_transposed` records
  * the orientation the caller applied (Diagnostics.transposed; ut/vt are swapped back accordingly).
+ * `comm` (borrowed, must outlive the operator) may be NULL for a single-rank run.
  * After solve each rank's result holds all of the N-side vectors and ITS OWN row slice of the M-side ones
  * (ut_cols or vt_cols == row_end-row_begin), so no collective is needed for them. */
 SVDLAS2_API int svdlas2_operator_create_shard(uint64_t m_global, uint64_t n, uint64_t row_begin, uint64_t row_end,
                                   uint64_t local_nnz, const uint64_t *local_offsets,
                                   const uint64_t *local_indices, const double *values, int b_is_a_transposed,
-                                  uint64_t global_nnz, int rank, int world_size,
-                                  const uint8_t id[SVDLAS2_COMM_ID_BYTES], int device, svdlas2_operator **op);
+                                  uint64_t global_nnz, svdlas2_comm *comm, int device, svdlas2_operator **op);
 
 #ifdef __cplusplus
 }

@@ -23,11 +23,16 @@ A, _ = synthetic.make(a.workload, scale=a.scale)
 B, transposed = sharding.orient(A)
 bounds = sharding.partition_rows_by_nnz(B.indptr, world)
 Bl, lo, hi = sharding.local_shard(B, bounds, rank)
-cid = sharding.broadcast_comm_id(dist, rank)
+comm = las2.Communicator(rank, world, sharding.broadcast_comm_id(dist, rank), device=local)
 t0 = time.time()
-with las2.ShardedOperator(Bl, B.shape[0], lo, int(B.nnz), rank, world, cid, transposed, device=local) as op:
+with las2.ShardedOperator(Bl, B.shape[0], lo, int(B.nnz), comm, transposed, device=local) as op:
     r = op.solve(a.dims, random_seed=12345)
     t_sharded = time.time() - t0
+    for rep in range(3):
+        rr = op.solve(a.dims, random_seed=12345)
+        if rank == 0:
+            print("PROFILE", rep, json.dumps({k: round(rr.profile[k], 4) for k in ("t_total", "t_lanczos", "t_sync_wait", "t_ritvec", "t_imtql2", "t_download", "t_device")}), flush=True)
+        del rr
     tm = op.time_opb(reps=10)
 # every rank must hold bit-identical N-side vectors and scalars
 sig = torch.tensor(r.s, device="cuda")

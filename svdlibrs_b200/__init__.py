@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["svd", "svd_dim", "svd_dim_seed", "svdLAS2", "SvdRec", "Diagnostics", "SvdLibError", "Operator", "RawMatrix",
-           "ShardedOperator", "comm_unique_id", "build"]
+           "ShardedOperator", "Communicator", "comm_unique_id", "build"]
 
 build = _lib.build
 
@@ -306,28 +306,49 @@ def comm_unique_id() -> bytes:
     return bytes(buf)
 
 
+class Communicator:
+    """Long-lived NCCL communicator of one rank (one process per GPU); serves any number of ShardedOperators."""
+
+    def __init__(self, rank: int, world_size: int, comm_id: Optional[bytes], device: int = -1):
+        idbuf = (C.c_uint8 * _lib.COMM_ID_BYTES)(*(comm_id or bytes(_lib.COMM_ID_BYTES)))
+        self._h = C.c_void_p()
+        rc = _lib.lib().svdlas2_comm_create(int(rank), int(world_size), idbuf, int(device), C.byref(self._h))
+        if rc != 0:
+            _raise(rc)
+        self.rank, self.world_size = rank, world_size
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().svdlas2_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
 class ShardedOperator(Operator):
     """One rank's row range [row_begin, row_end) of the oriented operator B: rows are partitioned by
     nnz over the GPUs of one box, y = sum_g B_g'(B_g x) is completed by one all-reduce of N doubles per opb."""
 
-    def __init__(self, local_csr, m_global: int, row_begin: int, global_nnz: int, rank: int, world_size: int,
-                 comm_id: Optional[bytes], b_is_a_transposed: bool = False, device: int = -1):
+    def __init__(self, local_csr, m_global: int, row_begin: int, global_nnz: int, comm: Optional["Communicator"],
+                 b_is_a_transposed: bool = False, device: int = -1):
         L = _lib.lib()
         if getattr(local_csr, "format", None) != "csr":
             raise TypeError("the shard must be a csr matrix holding rows [row_begin, row_end) of B")
         rows, n = local_csr.shape
         a, b, v = _u64(local_csr.indptr), _u64(local_csr.indices), _f64(local_csr.data)
-        idbuf = (C.c_uint8 * _lib.COMM_ID_BYTES)(*(comm_id or bytes(_lib.COMM_ID_BYTES)))
         self._h = C.c_void_p()
+        self._comm = comm  # keep the communicator alive as long as the operator
         rc = L.svdlas2_operator_create_shard(int(m_global), int(n), int(row_begin), int(row_begin + rows),
                                              int(local_csr.nnz), _ptr(a, C.c_uint64), _ptr(b, C.c_uint64),
-                                             _ptr(v, C.c_double), int(b_is_a_transposed), int(global_nnz), int(rank),
-                                             int(world_size), idbuf, int(device), C.byref(self._h))
+                                             _ptr(v, C.c_double), int(b_is_a_transposed), int(global_nnz),
+                                             comm._h if comm is not None else None, int(device), C.byref(self._h))
         if rc != 0:
             _raise(rc)
         self.shape_a = (n, m_global) if b_is_a_transposed else (m_global, n)
         self.m, self.n, self.nnz, self.transposed = rows, n, int(local_csr.nnz), bool(b_is_a_transposed)
-        self.m_global, self.row_begin, self.rank, self.world_size = m_global, row_begin, rank, world_size
+        self.m_global, self.row_begin = m_global, row_begin
+        self.rank = comm.rank if comm else 0
+        self.world_size = comm.world_size if comm else 1
 
     def opa(self, x, transposed: bool = False):
         raise SvdLibError(6, "opa is not available on a sharded operator")

@@ -51,7 +51,7 @@ SYMBOLS = [
     "svdlas2_csr", "svdlas2_csc", "svdlas2_coo", "svdlas2_free", "svdlas2_last_error", "svdlas2_abi_version",
     "svdlas2_operator_create", "svdlas2_operator_destroy", "svdlas2_operator_solve", "svdlas2_operator_opa",
     "svdlas2_operator_opb", "svdlas2_operator_shape", "svdlas2_operator_time_opb", "svdlas2_operator_set",
-    "svdlas2_comm_unique_id", "svdlas2_operator_create_shard",
+    "svdlas2_comm_unique_id", "svdlas2_comm_create", "svdlas2_comm_destroy", "svdlas2_operator_create_shard",
 ]
 
 
@@ -109,9 +109,12 @@ def lib():
     L.svdlas2_operator_set.restype = C.c_int
     L.svdlas2_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.svdlas2_comm_unique_id.restype = C.c_int
+    L.svdlas2_comm_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_void_p)]
+    L.svdlas2_comm_create.restype = C.c_int
+    L.svdlas2_comm_destroy.argtypes = [C.c_void_p]
+    L.svdlas2_comm_destroy.restype = None
     L.svdlas2_operator_create_shard.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p,
-                                                f64p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint8),
-                                                C.c_int, C.POINTER(OP)]
+                                                f64p, C.c_int, C.c_uint64, C.c_void_p, C.c_int, C.POINTER(OP)]
     L.svdlas2_operator_create_shard.restype = C.c_int
     _lib = L
     return L

@@ -271,16 +271,32 @@ int svdlas2_comm_unique_id(uint8_t id[SVDLAS2_COMM_ID_BYTES]) {
     return guarded([&] { Comm::unique_id(id); });
 }
 
+int svdlas2_comm_create(int rank, int world_size, const uint8_t id[SVDLAS2_COMM_ID_BYTES], int device,
+                        svdlas2_comm **comm) {
+    if (!comm) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "comm is null");
+    *comm = nullptr;
+    return guarded([&] {
+        if (world_size > 1 && !id) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "null communicator id");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            throw Error(SVDLAS2_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+        }
+        if (device >= 0) LAS2_CUDA(cudaSetDevice(device));
+        *comm = reinterpret_cast<svdlas2_comm *>(Comm::create(rank, world_size, id));
+    });
+}
+
+void svdlas2_comm_destroy(svdlas2_comm *comm) { delete reinterpret_cast<Comm *>(comm); }
+
 int svdlas2_operator_create_shard(uint64_t m_global, uint64_t n, uint64_t row_begin, uint64_t row_end,
                                   uint64_t local_nnz, const uint64_t *local_offsets, const uint64_t *local_indices,
-                                  const double *values, int b_is_a_transposed, uint64_t global_nnz, int rank,
-                                  int world_size, const uint8_t id[SVDLAS2_COMM_ID_BYTES], int device,
-                                  svdlas2_operator **out) {
+                                  const double *values, int b_is_a_transposed, uint64_t global_nnz, svdlas2_comm *comm,
+                                  int device, svdlas2_operator **out) {
     if (!out) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "op is null");
     *out = nullptr;
     return guarded([&] {
         if (row_end < row_begin || row_end > m_global) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "bad row range");
-        if (world_size > 1 && !id) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "null communicator id");
         std::unique_ptr<Operator> op(new Operator());
         select_device(device, *op);
         const double t0 = wall_now();
@@ -294,7 +310,8 @@ int svdlas2_operator_create_shard(uint64_t m_global, uint64_t n, uint64_t row_be
         op->N = n;
         build_operator_from_csr(op->M, n, local_nnz, local_offsets, local_indices, values, op->stream, op->B, op->BT,
                                 op->upload);
-        op->comm.reset(Comm::create(rank, world_size, id));
+        Comm *c = reinterpret_cast<Comm *>(comm);
+        op->comm = (c && c->world() > 1) ? c : nullptr;
         op->t_upload = wall_now() - t0;
         *out = reinterpret_cast<svdlas2_operator *>(op.release());
     });

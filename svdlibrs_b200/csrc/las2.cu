@@ -20,6 +20,8 @@
 #include <chrono>
 #include <future>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -31,6 +33,7 @@ namespace las2 {
 
 // vecops.cu
 void vec_sigma_scale(double *u, u64 m, const PartialSlot &t, double *sigma_out, cudaStream_t s);
+void vec_sumsq_any(const double *a, u64 n, PartialSlot &out, cudaStream_t s);
 
 namespace {
 
@@ -383,11 +386,16 @@ struct Solver {
         int rc = ql_rotations(js, dd.data(), ee.data(), plan);
         if (rc == SVDLAS2_ERR_IMTQL2) throw Error(rc, "imtql2 no convergence to an eigenvalue after 30 iterations");
         if (rc) throw Error(rc, "imtql2: expected 'm' to be non-zero");
+        const double tq1 = wall();
         const u32 ldz = (u32)round_up(js, 32);
         DevBuf<double> zT((size_t)ldz * js);
         ql_replay(plan, (u32)js, ldz, zT.get(), s, &prof.n_kernel_launches, &prof.h2d_bytes);
         LAS2_CUDA(cudaStreamSynchronize(s));
         *t_imtql2 = wall() - tq0;
+        if (std::getenv("SVDLAS2_TRACE"))
+            fprintf(stderr, "[svdlas2] imtql2: js=%llu rotations=%llu sweeps=%zu host %.4f s, device replay %.4f s\n",
+                    (unsigned long long)js, (unsigned long long)plan.rotations(), plan.sweeps.size(), tq1 - tq0,
+                    wall() - tq1);
 
         // acceptance (:1800-1801) in ascending eigenvalue order; the reference's circular buffer + rotate_array
         // keep the LAST `dims` accepted, largest first (:1802-1827)
@@ -429,7 +437,11 @@ struct Solver {
         Q.release(); // the panel is no longer needed; make room for U
         qcap = qused = 0;
 
-        // sigma_i = sqrt(v_i . B'B v_i), u_i = B v_i / sigma_i (:1839-1859).  B v_i is computed once and reused.
+        // sigma_i = sqrt(v_i . B'B v_i), u_i = B v_i / sigma_i (:1839-1859).  The reference applies the operator
+        // three times per triplet (B v and B'(B v) inside svd_opb for sigma, then B v again for u).  Here B v is
+        // computed ONCE: v . B'(B v) == (B v) . (B v), so sigma = |B v| and u = B v / sigma come from the same
+        // vector (a rounding-level difference in sigma, far inside the 1e-10 parity tolerance).  In a sharded run
+        // every rank holds its row slice of B v: the squared norms are completed by a one-double all-reduce.
         // Finished rows stream to the (pinned) result on a second stream while later rows are still computed.
         cudaEvent_t ev;
         LAS2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -440,20 +452,25 @@ struct Solver {
                                     cudaMemcpyDeviceToHost, copy_stream));
         DevBuf<double> U((size_t)d * mcols);
         DevBuf<double> S(d);
+        DevBuf<double> nrm2(d); // |B_g v_i|^2 per triplet (summed over ranks when sharded)
         for (u64 i = 0; i < d; i++) {
             double *vi = V.get() + i * ld;
             double *ui = U.get() + i * mcols;
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (op.profile) { LAS2_CUDA(cudaEventCreate(&e0)); LAS2_CUDA(cudaEventCreate(&e1)); LAS2_CUDA(cudaEventRecord(e0, s)); }
             spmv(op.B, vi, ui, s, &prof.n_kernel_launches);
-            spmv(op.BT, ui, r.get(), s, &prof.n_kernel_launches);
-            if (op.comm) op.comm->allreduce_sum(r.get(), N, s);
-            if (op.profile) { LAS2_CUDA(cudaEventRecord(e1, s)); opb_events.emplace_back(e0, e1); }
-            prof.n_opb += 1;
-            prof.n_spmv += 2;
-            vec_dot(vi, r.get(), ld, slot[0], s);
-            vec_sigma_scale(ui, mcols, slot[0], S.get() + i, s);
-            prof.n_kernel_launches += 2;
+            prof.n_spmv += 1;
+            vec_sumsq_any(ui, mcols, slot[0], s);
+            PartialSlot t2 = slot[0];
+            prof.n_kernel_launches += 1;
+            if (op.comm) {
+                GatherList g;
+                g.count = 1; g.parts[0] = slot[0].parts; g.nparts[0] = slot[0].nparts;
+                gather_scalars(g, nrm2.get() + i, s);
+                op.comm->allreduce_sum(nrm2.get() + i, 1, s);
+                t2 = PartialSlot{nrm2.get() + i, 1};
+                prof.n_kernel_launches += 1;
+            }
+            vec_sigma_scale(ui, mcols, t2, S.get() + i, s);
+            prof.n_kernel_launches += 1;
             LAS2_CUDA(cudaEventRecord(ev, s));
             LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
             LAS2_CUDA(cudaMemcpyAsync(hU + i * mcols, ui, mcols * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));

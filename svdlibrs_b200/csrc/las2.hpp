@@ -24,7 +24,7 @@ struct Operator {
     u64 N = 0;
     u64 row_begin = 0;
     DeviceCsr B, BT; // BT is N x M (local)
-    std::unique_ptr<Comm> comm; // null on a single GPU
+    Comm *comm = nullptr; // borrowed; null on a single GPU
     // scratch for opa/opb/time_opb
     DevBuf<double> tmp_m, tmp_x, tmp_y;
     DevBuf<char> l2_flush;

@@ -48,6 +48,54 @@ k_ql_replay(double *__restrict__ zT, u32 ldz, u32 js, const QlSweep *__restrict_
     }
 }
 
+// Same replay with the CTA's rows of z resident in shared memory (js x rpc doubles): the per-rotation load is an
+// LDS instead of an L2 round trip, which matters because the rotations of one row form a dependent chain.
+__global__ void k_ql_replay_smem(double *__restrict__ zT, u32 ldz, u32 js, u32 rpc, const QlSweep *__restrict__ sweeps,
+                                 u32 nsweeps, const double2 *__restrict__ sc) {
+    extern __shared__ double zs[]; // zs[col * rpc + local_row]
+    const u32 row0 = blockIdx.x * rpc;
+    for (u32 e = threadIdx.x; e < js * rpc; e += blockDim.x) {
+        const u32 col = e / rpc, lr = e % rpc;
+        zs[e] = (row0 + lr == col) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    // One warp replays: lane = local row.  The rotation parameters are the same for every row, so the warp
+    // fetches them 32 at a time (one coalesced 512-byte load, prefetched one batch ahead) and broadcasts them
+    // with shuffles instead of stalling on a uniform global load per rotation.
+    if (threadIdx.x < 32) {
+        const u32 lane = threadIdx.x;
+        const bool live = lane < rpc && row0 + lane < js;
+        double *z = zs + (live ? lane : 0);
+        for (u32 w = 0; w < nsweeps; w++) {
+            const QlSweep sw = sweeps[w];
+            const double2 *__restrict__ rot = sc + sw.first;
+            u32 i = sw.hi;
+            double carry = z[(i + 1) * rpc];
+            double2 nxt = (lane < sw.count) ? rot[lane] : make_double2(0.0, 0.0);
+            for (u32 t0 = 0; t0 < sw.count; t0 += 32) {
+                const double2 cur = nxt;
+                if (t0 + 32 + lane < sw.count) nxt = rot[t0 + 32 + lane];
+                const u32 nb = min(32u, sw.count - t0);
+#pragma unroll 4
+                for (u32 t = 0; t < nb; t++, i--) {
+                    const double ps = __shfl_sync(0xffffffffu, cur.x, t);
+                    const double pc = __shfl_sync(0xffffffffu, cur.y, t);
+                    const double x = z[i * rpc];
+                    const double hi_new = __dadd_rn(__dmul_rn(ps, x), __dmul_rn(pc, carry));
+                    carry = __dsub_rn(__dmul_rn(pc, x), __dmul_rn(ps, carry));
+                    if (live) z[(i + 1) * rpc] = hi_new;
+                }
+            }
+            if (live) z[(u32)(i + 1) * rpc] = carry;
+        }
+    }
+    __syncthreads();
+    for (u32 e = threadIdx.x; e < js * rpc; e += blockDim.x) {
+        const u32 col = e / rpc, r = e % rpc;
+        if (row0 + r < js) zT[(u64)col * ldz + row0 + r] = zs[e];
+    }
+}
+
 __global__ void k_ritz_coefficients(const double *__restrict__ zT, u32 ldz, u32 js, const u32 *__restrict__ phys,
                                     u32 d, double *__restrict__ C) {
     u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,10 +107,16 @@ __global__ void k_ritz_coefficients(const double *__restrict__ zT, u32 ldz, u32 
 } // namespace
 
 void ql_replay(const QlPlan &plan, u32 js, u32 ldz, double *zT, cudaStream_t s, u64 *launches, u64 *h2d_bytes) {
-    unsigned g = cdiv((u64)ldz * js, 256);
-    if (g > (unsigned)kNumSMs * 16) g = kNumSMs * 16;
-    k_identity<<<g, 256, 0, s>>>(zT, ldz, js);
-    if (launches) *launches += 1;
+    // rows of z per CTA such that js x rpc doubles fit in shared memory (largest power of two <= 32)
+    u32 rpc = 32;
+    while (rpc > 4 && (size_t)js * rpc * sizeof(double) > 200 * 1024) rpc >>= 1;
+    const bool in_smem = (size_t)js * rpc * sizeof(double) <= 200 * 1024;
+    if (!in_smem || plan.sweeps.empty()) {
+        unsigned g = cdiv((u64)ldz * js, 256);
+        if (g > (unsigned)kNumSMs * 16) g = kNumSMs * 16;
+        k_identity<<<g, 256, 0, s>>>(zT, ldz, js);
+        if (launches) *launches += 1;
+    }
     if (!plan.sweeps.empty()) {
         DevBuf<QlSweep> dsw(plan.sweeps.size());
         DevBuf<double> dsc(plan.sc.size());
@@ -70,8 +124,19 @@ void ql_replay(const QlPlan &plan, u32 js, u32 ldz, double *zT, cudaStream_t s, 
                                   cudaMemcpyHostToDevice, s));
         LAS2_CUDA(cudaMemcpyAsync(dsc.get(), plan.sc.data(), plan.sc.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         if (h2d_bytes) *h2d_bytes += plan.sweeps.size() * sizeof(QlSweep) + plan.sc.size() * sizeof(double);
-        k_ql_replay<<<cdiv(js, kReplayThreads), kReplayThreads, 0, s>>>(zT, ldz, js, dsw, (u32)plan.sweeps.size(),
-                                                                      reinterpret_cast<const double2 *>(dsc.get()));
+        if (in_smem) {
+            const size_t bytes = (size_t)js * rpc * sizeof(double);
+            static bool attr_set = false;
+            if (!attr_set) {
+                LAS2_CUDA(cudaFuncSetAttribute(k_ql_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set = true;
+            }
+            k_ql_replay_smem<<<cdiv(js, rpc), 128, bytes, s>>>(zT, ldz, js, rpc, dsw, (u32)plan.sweeps.size(),
+                                                               reinterpret_cast<const double2 *>(dsc.get()));
+        } else {
+            k_ql_replay<<<cdiv(js, kReplayThreads), kReplayThreads, 0, s>>>(zT, ldz, js, dsw, (u32)plan.sweeps.size(),
+                                                                          reinterpret_cast<const double2 *>(dsc.get()));
+        }
         LAS2_LAUNCH_CHECK();
         if (launches) *launches += 1;
         LAS2_CUDA(cudaStreamSynchronize(s)); // dsw / dsc are freed on scope exit

@@ -92,6 +92,20 @@ k_axpy_dot(double2 *__restrict__ r, const double2 *__restrict__ x, Coef coef, co
     }
 }
 
+// partial sums of a . a for a vector of arbitrary length and alignment (the rows of U are M doubles apart)
+__global__ void __launch_bounds__(kVecThreads) k_sumsq_any(const double *__restrict__ a, u64 n, double *__restrict__ out) {
+    __shared__ double sm[kVecThreads / 32];
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (; i < n; i += stride) {
+        const double v = a[i];
+        acc = fma(v, v, acc);
+    }
+    double s = cta_reduce(acc, sm);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 // sigma = sqrt(t), u *= 1/sigma  (ritvec tail, src/lib.rs:1851, 1858); t arrives as partials
 __global__ void __launch_bounds__(kVecThreads)
 k_sigma_scale(double *__restrict__ u, u64 m, const double *__restrict__ parts, int nparts, double *__restrict__ sigma_out) {
@@ -150,6 +164,15 @@ void vec_axpy_dot(double *r, const double *x, Coef coef, const double *y, u64 ld
 void vec_axpy(double *r, const double *x, Coef coef, u64 ld, cudaStream_t s) {
     k_axpy_dot<false><<<vec_grid(ld), kVecThreads, 0, s>>>((double2 *)r, (const double2 *)x, coef, nullptr, ld / 2,
                                                            nullptr);
+    LAS2_LAUNCH_CHECK();
+}
+
+void vec_sumsq_any(const double *a, u64 n, PartialSlot &out, cudaStream_t s) {
+    u64 g = (n + kVecThreads * 4 - 1) / (kVecThreads * 4);
+    if (g < 1) g = 1;
+    if (g > (u64)kMaxParts) g = kMaxParts;
+    k_sumsq_any<<<(unsigned)g, kVecThreads, 0, s>>>(a, n, out.parts);
+    out.nparts = (int)g;
     LAS2_LAUNCH_CHECK();
 }
 
