@@ -9,11 +9,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--blocked", default="0")
 a = ap.parse_args()
+os.environ['SVDLAS2_BLOCKED'] = a.blocked
 A, dims = synthetic.make(a.workload, scale=a.scale)
 print(json.dumps(dict(workload=a.workload, shape=list(A.shape), nnz=int(A.nnz))))
 with las2.Operator(A) as op:
-    for variant, hot in [(4, -1), (3, -1), (2, -1), (4, -1)]:
+    for variant, hot in ([(4, -1), (4, 1024), (4, 2048), (4, 3072), (4, 6144), (3, -1)] if a.blocked != '0' else [(3, -1), (2, -1)]):
         op.set("spmv_variant", variant); op.set("spmv_hot", hot)
         t = op.time_opb(reps=a.reps, flush_l2=False)
         print(json.dumps(dict(variant=variant, hot=hot, ms_opb=round(t["ms_per_opb"], 4), ms_b=round(t["ms_spmv_b"], 4),

@@ -199,6 +199,8 @@ int svdlas2_operator_opa(svdlas2_operator *op_, const double *x, double *y, int 
         const DeviceCsr &Mx = use_b ? op->B : op->BT;
         DevBuf<double> dx(Mx.cols ? Mx.cols : 1), dy(Mx.rows ? Mx.rows : 1);
         LAS2_CUDA(cudaMemcpyAsync(dx.get(), x, Mx.cols * sizeof(double), cudaMemcpyHostToDevice, op->stream));
+        // poison the output (NaN pattern): a row the kernel forgets to write must not look plausible
+        LAS2_CUDA(cudaMemsetAsync(dy.get(), 0xff, Mx.rows * sizeof(double), op->stream));
         spmv(Mx, dx.get(), dy.get(), op->stream);
         LAS2_CUDA(cudaMemcpyAsync(y, dy.get(), Mx.rows * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
         LAS2_CUDA(cudaStreamSynchronize(op->stream));
@@ -263,6 +265,7 @@ int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value)
     if (!std::strcmp(knob, "profile")) { op->profile = value != 0; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_variant")) { g_spmv_variant = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_hot")) { g_spmv_hot_entries = (int)value; return SVDLAS2_OK; }
+    if (!std::strcmp(knob, "spmv_tma")) { g_spmv_tma = (int)value; return SVDLAS2_OK; }
     return fail(SVDLAS2_ERR_INVALID_ARGUMENT, std::string("unknown knob ") + knob);
 }
 

@@ -94,10 +94,15 @@ inline u64 round_up_tile(u64 v) { return (v + kBlkTile - 1) / kBlkTile * kBlkTil
 void build_blocked(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
     BlockedCsr &K = X.blk;
     K = BlockedCsr();
-    // Experimental (round 1): correct and parity-tested, but not yet faster than the plain-CSR kernels on B200
-    // (profiles/r1_spmv_iterations.md), so it is only built on request.
+    // Modes (env SVDLAS2_BLOCKED): unset = auto: the interleaved 32-bit stream WITHOUT slabs for matrices large
+    // enough to fill the persistent kernel (profiles/r1_spmv_iterations.md: fastest on B200 so far); 0 = never;
+    // 1 = slabs where they pay (experimental: the per-(slab,row) bookkeeping costs more than it saves at LSA
+    // densities); 2 = no slabs, always.
     const char *want = std::getenv("SVDLAS2_BLOCKED");
-    if (!want || want[0] != '1') return;
+    const char mode = (want && want[0]) ? want[0] : 'a';
+    if (mode == '0') return;
+    if (mode == 'a' && X.nnz < (u64)8 * kNumSMs * kSpmvTile) return;
+    const bool no_slabs = mode != '1';
     if (X.nnz == 0 || X.rows == 0) return;
     const u32 nblocks = cdiv(X.cols, kBlockWidth);
     if (nblocks > 12000) return; // shared histogram limit; such matrices are far too sparse per block anyway
@@ -119,13 +124,13 @@ void build_blocked(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
     // 2. longest prefix of blocks that pays: include block b while it holds >= kMinPerRow entries per row
     u32 nbk = 0;
     u64 in_slabs = 0;
-    while (nbk < nblocks && (double)hist[nbk] >= kMinPerRow * (double)X.rows) { in_slabs += hist[nbk]; nbk++; }
+    while (!no_slabs && nbk < nblocks && (double)hist[nbk] >= kMinPerRow * (double)X.rows) { in_slabs += hist[nbk]; nbk++; }
     // a long, nearly uniform tail (B' of an LSA matrix) oscillates around the threshold: judge it as a whole
-    if (nbk < nblocks) {
+    if (!no_slabs && nbk < nblocks) {
         u64 rest = X.nnz - in_slabs;
         if ((double)rest >= kMinPerRow * (double)X.rows * (double)(nblocks - nbk)) { nbk = nblocks; in_slabs = X.nnz; }
     }
-    if (nbk == 0) return;
+    if (nbk == 0 && !no_slabs) return;
     const bool has_rem = in_slabs < X.nnz;
     const u32 nslabs = nbk + (has_rem ? 1 : 0);
     const u64 vrows = (u64)nslabs * X.rows;

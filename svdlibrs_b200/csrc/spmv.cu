@@ -16,6 +16,8 @@
 // Algorithmic bytes per launch: 12*Z + 4*(R+1) + 8*C + 8*R.
 #include "spmv.cuh"
 
+#include <algorithm>
+
 namespace las2 {
 
 namespace {
@@ -252,10 +254,11 @@ k_spmv_hot(const u32 *__restrict__ off, const u32 *__restrict__ idx, const doubl
 // tiles.  Each CTA takes a contiguous range of the slab tiles (one or two column blocks -> one or two loads of
 // the x slice) and an interleaved share of the remainder tiles (32-bit columns, gathered through L1/L2).
 // Output: one partial per virtual row (slab, row); k_slab_reduce adds the slabs of a row in slab order.
-constexpr int kBlkGroups = 5;
+constexpr int kBlkGroupsSlab = 5;  // beside the 128 KB slice of x
+constexpr int kBlkGroupsPlain = 8; // no slabs: only the (<= 64 KB) hot prefix of x is resident
+constexpr u32 kPlainHotDefault = 4096; // sweep on cfg 2: 4096 entries beat 8192 (more L1 left for the cold gathers)
 constexpr int kBlkLanes = 128; // threads per group
 constexpr int kBlkE = kBlkTile / kBlkLanes; // 8 consecutive elements per lane
-constexpr int kBlkThreads = kBlkGroups * kBlkLanes;
 constexpr int kBlkWarps = kBlkLanes / 32;
 constexpr int kBlkRowChunk = 256;
 constexpr int kBlkRoffPerThread = (kBlkRowChunk + 1 + kBlkLanes - 1) / kBlkLanes; // 3
@@ -300,8 +303,8 @@ __device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int t, u32 &par
                                          const u32 *__restrict__ voff, const uint16_t *__restrict__ idx16,
                                          const u32 *__restrict__ idx32, u32 rem_tile0, const double *__restrict__ val,
                                          const u32 *__restrict__ tile_row, const double *__restrict__ x,
-                                         const double *xs, double *__restrict__ out, double *__restrict__ carry,
-                                         double *__restrict__ head, u32 vrows, u64 pol_stream, u64 pol_keep) {
+                                         const double *xs, u32 hot, double *__restrict__ out, double *__restrict__ carry,
+                                         double *__restrict__ head, u32 vrows, u64 pol_stream, u64 pol_keep, bool use_tma) {
     constexpr u32 kIdxBytes = SLAB ? kBlkTile * 2 : kBlkTile * 4;
     const int lane = t & 31, warp = t >> 5;
     auto issue = [&](u32 tile) {
@@ -311,7 +314,7 @@ __device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int t, u32 &par
         else tma_load_1d(S.sidx, idx32 + (u64)(tile - rem_tile0) * kBlkTile, kIdxBytes, &S.full_bar, pol_stream);
     };
     if (first >= stop) return;
-    if (t == 0) issue(first);
+    if (t == 0 && use_tma) issue(first);
     for (u32 tile = first; tile < stop; tile += step) {
         const u32 start = tile * kBlkTile, end = start + kBlkTile;
         const u32 R0 = tile_row[tile], R1 = tile_row[tile + 1];
@@ -324,8 +327,15 @@ __device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int t, u32 &par
             const u32 e = t + i * kBlkLanes;
             ro[i] = (e <= nr0) ? voff[R0 + e] : 0u;
         }
-        mbar_wait(&S.full_bar, parity);
-        parity ^= 1u;
+        if (use_tma) {
+            mbar_wait(&S.full_bar, parity);
+            parity ^= 1u;
+        } else { // debugging path: cooperative copy instead of the bulk copy
+            for (int e = t; e < (int)kBlkTile; e += kBlkLanes) S.sval[e] = val[(u64)tile * kBlkTile + e];
+            if (SLAB) { for (int e = t; e < (int)kBlkTile; e += kBlkLanes) reinterpret_cast<uint16_t *>(S.sidx)[e] = idx16[(u64)tile * kBlkTile + e]; }
+            else { for (int e = t; e < (int)kBlkTile; e += kBlkLanes) S.sidx[e] = idx32[(u64)(tile - rem_tile0) * kBlkTile + e]; }
+            blk_group_sync(g);
+        }
         // ---- stage -> registers: slot k*128 + t holds element t*8 + k ----
         double p[kBlkE];
         u32 c[kBlkE];
@@ -340,8 +350,19 @@ __device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int t, u32 &par
             const u32 e = t + i * kBlkLanes;
             if (e <= nr0) S.roff[e] = ro[i];
         }
+        {
+            // A warp may ARRIVE at the barrier with its shared-memory loads of the stage still queued behind other
+            // warps' uncoalesced gathers (the LSU queue is in-order and a 32-line gather holds it for 32 cycles), and
+            // the bulk copy issued right after the barrier would then overwrite the stage under them (seen on B200
+            // as a handful of wrong rows per 45 M non-zeros).  A branch on the loaded values forces every stage
+            // read to COMPLETE before the barrier; it is never taken.
+            u32 chk = 0;
+#pragma unroll
+            for (int k = 0; k < kBlkE; k++) chk ^= c[k] ^ (u32)__double2loint(p[k]) ^ (u32)__double2hiint(p[k]);
+            if (chk == 0x9e3779b9u && c[0] == 0xffffffffu) S.flags[0] = 0xffffffffu;
+        }
         blk_group_sync(g); // stage consumed, flags cleared, first row chunk staged
-        if (t == 0 && tile + step < stop) issue(tile + step);
+        if (t == 0 && use_tma && tile + step < stop) issue(tile + step);
         // ---- gathers + products (registers only) ----
         if (SLAB) {
 #pragma unroll
@@ -349,7 +370,10 @@ __device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int t, u32 &par
         } else {
             double xv[kBlkE];
 #pragma unroll
-            for (int k = 0; k < kBlkE; k++) xv[k] = ld_gather_f64(x + c[k], pol_keep);
+            for (int k = 0; k < kBlkE; k++) {
+                if (c[k] < hot) xv[k] = xs[c[k]];
+                else xv[k] = ld_gather_f64(x + c[k], pol_keep);
+            }
 #pragma unroll
             for (int k = 0; k < kBlkE; k++) p[k] *= xv[k];
         }
@@ -435,11 +459,14 @@ __device__ __forceinline__ void blk_walk(BlkGroupSmem &S, int g, int t, u32 &par
     }
 }
 
-__global__ void __launch_bounds__(kBlkThreads, 1)
+template <int GROUPS>
+__global__ void __launch_bounds__(GROUPS * kBlkLanes, 1)
 k_spmv_blocked(const u32 *__restrict__ voff, const uint16_t *__restrict__ idx16, const u32 *__restrict__ idx32,
                const double *__restrict__ val, const u32 *__restrict__ tile_row, const u32 *__restrict__ slab_tile_start,
                const double *__restrict__ x, double *__restrict__ out, double *__restrict__ carry,
-               double *__restrict__ head, u32 vrows, u32 cols, u32 nbk, u32 blocked_tiles, u32 num_tiles) {
+               double *__restrict__ head, u32 vrows, u32 cols, u32 nbk, u32 blocked_tiles, u32 num_tiles, u32 hot, int use_tma) {
+    constexpr int kBlkGroups = GROUPS;
+    constexpr int kBlkThreads = GROUPS * kBlkLanes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlkGroupSmem *groups = reinterpret_cast<BlkGroupSmem *>(smem_raw);
     double *xs = reinterpret_cast<double *>(smem_raw + sizeof(BlkGroupSmem) * kBlkGroups);
@@ -468,13 +495,19 @@ k_spmv_blocked(const u32 *__restrict__ voff, const uint16_t *__restrict__ idx16,
         for (u32 i = threadIdx.x; i < kBlockWidth; i += kBlkThreads)
             xs[i] = (c0 + i < cols) ? ld_gather_f64(x + c0 + i, pol_keep) : 0.0;
         __syncthreads();
-        blk_walk<true>(S, g, t, parity, tt + g, t_stop, kBlkGroups, voff, idx16, idx32, blocked_tiles, val, tile_row, x, xs,
-                       out, carry, head, vrows, pol_stream, pol_keep);
+        blk_walk<true>(S, g, t, parity, tt + g, t_stop, kBlkGroups, voff, idx16, idx32, blocked_tiles, val, tile_row, x, xs, 0u,
+                       out, carry, head, vrows, pol_stream, pol_keep, use_tma != 0);
         tt = t_stop;
     }
-    // ---- remainder tiles: interleaved share of [blocked_tiles, num_tiles), gathers through L1/L2 ----
+    // ---- remainder tiles: interleaved share of [blocked_tiles, num_tiles), gathers through L1/L2 except for
+    //      the hot prefix of x (only when there are no slabs: the slice buffer is free then) ----
+    if (nbk == 0 && hot > 0) {
+        for (u32 i = threadIdx.x; i < hot; i += kBlkThreads) xs[i] = ld_gather_f64(x + i, pol_keep);
+        __syncthreads();
+    }
     blk_walk<false>(S, g, t, parity, blocked_tiles + blockIdx.x * kBlkGroups + g, num_tiles, gridDim.x * kBlkGroups, voff,
-                    idx16, idx32, blocked_tiles, val, tile_row, x, xs, out, carry, head, vrows, pol_stream, pol_keep);
+                    idx16, idx32, blocked_tiles, val, tile_row, x, xs, nbk == 0 ? hot : 0u, out, carry, head, vrows,
+                    pol_stream, pol_keep, use_tma != 0);
 }
 
 // y[r] = partial[0*R + r] + partial[1*R + r] + ... (slab order)
@@ -511,6 +544,7 @@ __global__ void k_spmv_fixup(const u32 *__restrict__ off, const u32 *__restrict_
 
 int g_spmv_variant = -1;
 int g_spmv_hot_entries = -1; // -1 auto
+int g_spmv_tma = 1;          // 0: debugging path without bulk copies
 
 namespace {
 constexpr u32 kHotMaxEntries = 16384; // upper bound of the knob: 128 KB of the 227 KB
@@ -520,20 +554,34 @@ bool g_hot_attr_set = false;
 
 namespace {
 bool g_blk_attr_set = false;
-size_t blk_smem_bytes() { return sizeof(BlkGroupSmem) * kBlkGroups + (size_t)kBlockWidth * sizeof(double); }
+size_t blk_smem_bytes(int groups, u32 xs_entries) { return sizeof(BlkGroupSmem) * groups + (size_t)xs_entries * sizeof(double); }
 
 void spmv_blocked(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
     const BlockedCsr &K = A.blk;
     if (!g_blk_attr_set) {
-        LAS2_CUDA(cudaFuncSetAttribute(k_spmv_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_smem_bytes()));
+        LAS2_CUDA(cudaFuncSetAttribute(k_spmv_blocked<kBlkGroupsSlab>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)blk_smem_bytes(kBlkGroupsSlab, kBlockWidth)));
+        LAS2_CUDA(cudaFuncSetAttribute(k_spmv_blocked<kBlkGroupsPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)blk_smem_bytes(kBlkGroupsPlain, kHotPrefix)));
         g_blk_attr_set = true;
     }
     double *out = K.nslabs > 1 ? K.partial.get() : y;
-    u32 grid = kNumSMs;
-    if (grid * kBlkGroups > K.num_tiles) grid = cdiv(K.num_tiles, kBlkGroups);
-    k_spmv_blocked<<<grid, kBlkThreads, blk_smem_bytes(), s>>>(K.voff, K.idx16, K.idx32, K.val, K.tile_row,
-                                                              K.slab_tile_start, x, out, K.carry, K.head, (u32)K.vrows,
-                                                              (u32)K.cols, K.nbk, K.blocked_tiles, K.num_tiles);
+    if (K.nbk > 0) {
+        u32 grid = kNumSMs;
+        if (grid * kBlkGroupsSlab > K.num_tiles) grid = cdiv(K.num_tiles, kBlkGroupsSlab);
+        k_spmv_blocked<kBlkGroupsSlab><<<grid, kBlkGroupsSlab * kBlkLanes, blk_smem_bytes(kBlkGroupsSlab, kBlockWidth), s>>>(
+            K.voff, K.idx16, K.idx32, K.val, K.tile_row, K.slab_tile_start, x, out, K.carry, K.head, (u32)K.vrows,
+            (u32)K.cols, K.nbk, K.blocked_tiles, K.num_tiles, 0u, g_spmv_tma);
+    } else {
+        u32 hot = g_spmv_hot_entries >= 0 ? (u32)g_spmv_hot_entries : std::min<u32>(A.hot_entries, kPlainHotDefault);
+        if (hot > kHotPrefix) hot = kHotPrefix;
+        if (hot > K.cols) hot = (u32)K.cols;
+        u32 grid = kNumSMs;
+        if (grid * kBlkGroupsPlain > K.num_tiles) grid = cdiv(K.num_tiles, kBlkGroupsPlain);
+        k_spmv_blocked<kBlkGroupsPlain><<<grid, kBlkGroupsPlain * kBlkLanes, blk_smem_bytes(kBlkGroupsPlain, hot), s>>>(
+            K.voff, K.idx16, K.idx32, K.val, K.tile_row, K.slab_tile_start, x, out, K.carry, K.head, (u32)K.vrows,
+            (u32)K.cols, K.nbk, K.blocked_tiles, K.num_tiles, hot, g_spmv_tma);
+    }
     if (K.num_tiles > 1) {
         k_spmv_fixup<<<cdiv(K.num_tiles - 1, 128), 128, 0, s>>>(K.voff, K.tile_row, K.carry, K.head, out, K.num_tiles, kBlkTile);
         if (launches) *launches += 1;

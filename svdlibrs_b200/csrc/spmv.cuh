@@ -5,6 +5,7 @@
 namespace las2 {
 
 extern int g_spmv_variant;     // -1 auto; test / tuning override (svdlas2_operator_set "spmv_variant")
+extern int g_spmv_tma;
 extern int g_spmv_hot_entries; // -1 auto; entries of the gathered vector kept in shared memory ("spmv_hot")
 
 // y = A x on stream s.  x: A.cols doubles, y: A.rows doubles, both device-resident, no aliasing.
