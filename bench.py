@@ -285,7 +285,7 @@ def run_ours(args):
         t = json.load(open(tp))
         if t.get("workload") == info["name"] and t.get("scale") == info["scale"]:
             traffic = t.get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_spmv_stream (2 launches per opb: B then B')", "achieved": ach,
+    roofline = {"bound": "hbm", "kernel": "k_spmv_blocked<8> / k_spmv_stream (2 launches per opb: B then B')", "achieved": ach,
                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": tm["bytes_opb"] / 2, "ms_per_launch": tm["ms_per_opb"] / 2,
                 "spmv_b": {"GB/s": tm["bytes_spmv_b"] / tm["ms_spmv_b"] / 1e6, "ms": tm["ms_spmv_b"]},

@@ -20,6 +20,8 @@ namespace las2 {
 void exclusive_scan_u32(u32 *data, u64 n, cudaStream_t s, UploadStats &st); // device_csr.cu
 void expand_row_ids(const u32 *off, u32 rows, u64 nnz, u32 *rowid, cudaStream_t s, UploadStats &st);
 void build_tile_rows(const u32 *off, u32 rows, u64 nnz, u32 num_tiles, u32 tile, u32 *tile_row, cudaStream_t s, UploadStats &st);
+void build_fix_list(const u32 *off, const u32 *tile_row, u32 num_tiles, u32 tile, u32 *fix_row, u32 *fix_first,
+                    cudaStream_t s, UploadStats &st);
 
 namespace {
 
@@ -141,14 +143,17 @@ void build_blocked(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
     expand_row_ids(X.off, (u32)X.rows, X.nnz, rowid, s, st);
     K.voff.alloc(vrows + 1);
     LAS2_CUDA(cudaMemsetAsync(K.voff.get(), 0, (vrows + 1) * sizeof(u32), s));
-    {
+    if (nbk == 0) {
+        // one slab holding everything: the positions are the row offsets themselves
+        LAS2_CUDA(cudaMemcpyAsync(K.voff.get(), X.off.get(), (X.rows + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+    } else {
         unsigned grid = cdiv(X.nnz, 256 * 4);
         if (grid > (unsigned)kNumSMs * 16) grid = kNumSMs * 16;
         k_vrow_count<<<grid, 256, 0, s>>>(X.idx, rowid, X.nnz, nbk, X.rows, K.voff);
         LAS2_LAUNCH_CHECK();
         st.launches++;
+        exclusive_scan_u32(K.voff, vrows + 1, s, st);
     }
-    exclusive_scan_u32(K.voff, vrows + 1, s, st);
     // slab starts (unpadded) -> tile-padded starts
     std::vector<u32> starts(nslabs + 1);
     for (u32 i = 0; i <= nslabs; i++)
@@ -200,6 +205,9 @@ void build_blocked(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
     LAS2_CUDA(cudaMemcpyAsync(K.slab_tile_start.get(), tile_start.data(), (nslabs + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
     K.carry.alloc(K.num_tiles);
     K.head.alloc(K.num_tiles);
+    K.fix_row.alloc(K.num_tiles);
+    K.fix_first.alloc(K.num_tiles);
+    build_fix_list(K.voff, K.tile_row, K.num_tiles, kBlkTile, K.fix_row, K.fix_first, s, st);
     if (nslabs > 1) K.partial.alloc(vrows);
     LAS2_CUDA(cudaStreamSynchronize(s)); // rowid, dshift, host vectors go out of scope
 

@@ -306,6 +306,23 @@ __global__ void k_count_below(const u32 *__restrict__ idx, u64 nnz, u32 limit, u
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// fix_row[b] = the row whose last piece is the head of tile b (it began in tile fix_first[b] < b), or ~0u
+__global__ void k_fix_list(const u32 *__restrict__ off, const u32 *__restrict__ tile_row, u32 num_tiles, u32 tile,
+                           u32 *__restrict__ fix_row, u32 *__restrict__ fix_first) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num_tiles) return;
+    u32 row = 0xffffffffu, first = 0;
+    if (b > 0) {
+        const u32 R0 = tile_row[b], R1 = tile_row[b + 1];
+        if (R0 < R1) {
+            const u32 o0 = off[R0];
+            if (o0 < b * tile) { row = R0; first = o0 / tile; }
+        }
+    }
+    fix_row[b] = row;
+    fix_first[b] = first;
+}
+
 inline u64 pad_to_tile(u64 nnz) { return ((nnz + kSpmvTile - 1) / kSpmvTile) * kSpmvTile + kSpmvTile; }
 
 void finish_csr(DeviceCsr &M, cudaStream_t s, UploadStats &st) {
@@ -321,6 +338,11 @@ void finish_csr(DeviceCsr &M, cudaStream_t s, UploadStats &st) {
     M.carry.alloc(M.num_tiles);
     M.head.alloc(M.num_tiles);
     k_tile_rows<<<cdiv(M.num_tiles + 1, 256), 256, 0, s>>>(M.off, (u32)M.rows, M.nnz, M.num_tiles, kSpmvTile, M.tile_row);
+    LAS2_LAUNCH_CHECK();
+    st.launches++;
+    M.fix_row.alloc(M.num_tiles);
+    M.fix_first.alloc(M.num_tiles);
+    k_fix_list<<<cdiv(M.num_tiles, 256), 256, 0, s>>>(M.off, M.tile_row, M.num_tiles, kSpmvTile, M.fix_row, M.fix_first);
     LAS2_LAUNCH_CHECK();
     st.launches++;
     // is a shared-memory prefix of the gathered vector worth it for this matrix?
@@ -422,6 +444,12 @@ void expand_row_ids(const u32 *off, u32 rows, u64 nnz, u32 *rowid, cudaStream_t 
 }
 void build_tile_rows(const u32 *off, u32 rows, u64 nnz, u32 num_tiles, u32 tile, u32 *tile_row, cudaStream_t s, UploadStats &st) {
     k_tile_rows<<<cdiv(num_tiles + 1, 256), 256, 0, s>>>(off, rows, nnz, num_tiles, tile, tile_row);
+    LAS2_LAUNCH_CHECK();
+    st.launches++;
+}
+void build_fix_list(const u32 *off, const u32 *tile_row, u32 num_tiles, u32 tile, u32 *fix_row, u32 *fix_first,
+                    cudaStream_t s, UploadStats &st) {
+    k_fix_list<<<cdiv(num_tiles, 256), 256, 0, s>>>(off, tile_row, num_tiles, tile, fix_row, fix_first);
     LAS2_LAUNCH_CHECK();
     st.launches++;
 }

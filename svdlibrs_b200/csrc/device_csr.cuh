@@ -41,6 +41,7 @@ struct BlockedCsr {
     DevBuf<u32> tile_row;    // num_tiles + 1 (virtual rows)
     DevBuf<u32> slab_tile_start; // nslabs + 1
     DevBuf<double> carry, head;  // num_tiles
+    DevBuf<u32> fix_row, fix_first; // num_tiles: row completed by the fix-up of tile b (or ~0u) and its first tile
     DevBuf<double> partial;      // vrows (unused when nslabs == 1)
     u64 stream_bytes = 0;        // bytes one SpMV actually moves (for reporting)
 };
@@ -57,6 +58,7 @@ struct DeviceCsr {
     DevBuf<u32> tile_row;  // num_tiles + 1: first row that ENDS after the tile's first nnz (tile_row[0] = 0)
     DevBuf<double> carry;  // num_tiles: partial sum of the row that continues into the next tile
     DevBuf<double> head;   // num_tiles: partial sum of the tile's first row when it began in an earlier tile
+    DevBuf<u32> fix_row, fix_first; // num_tiles: row completed by the fix-up of tile b (or ~0u) and its first tile
     // hot prefix of the gathered vector: entries [0, hot_entries) are worth keeping in shared memory when a
     // large share of the column indices falls there (measured at upload: hot_fraction)
     u32 hot_entries = 0;

@@ -521,23 +521,20 @@ __global__ void k_slab_reduce(const double *__restrict__ partial, u64 rows, u32 
     }
 }
 
-// Rows that straddle tile boundaries: y[r] = carry[b0] + ... + carry[b-1] + head[b], b = the tile the row ends in.
-__global__ void k_spmv_fixup(const u32 *__restrict__ off, const u32 *__restrict__ tile_row,
+// Rows that straddle tile boundaries: y[row] = carry[first] + ... + carry[b-1] + head[b], b = the tile the row
+// ends in.  (row, first) per tile are precomputed at upload (k_fix_list), so this is two dependent load levels.
+__global__ void k_spmv_fixup(const u32 *__restrict__ fix_row, const u32 *__restrict__ fix_first,
                              const double *__restrict__ carry, const double *__restrict__ head,
-                             double *__restrict__ y, u32 num_tiles, u32 tile_nnz) {
-    u32 b = blockIdx.x * blockDim.x + threadIdx.x + 1;
+                             double *__restrict__ y, u32 num_tiles) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (b >= num_tiles) return;
-    const u32 R0 = tile_row[b], R1 = tile_row[b + 1];
-    const u32 start = b * tile_nnz;
-    if (R0 < R1) {
-        const u32 o0 = off[R0];
-        if (o0 < start) {
-            double s = 0.0;
-            for (u32 t = o0 / tile_nnz; t < b; t++) s += carry[t];
-            s += head[b];
-            y[R0] = s;
-        }
-    }
+    const u32 row = fix_row[b];
+    if (row == 0xffffffffu) return;
+    const u32 first = fix_first[b];
+    const double h = head[b];
+    double s = 0.0;
+    for (u32 t = first; t < b; t++) s += carry[t];
+    y[row] = s + h;
 }
 
 } // namespace
@@ -583,7 +580,7 @@ void spmv_blocked(const DeviceCsr &A, const double *x, double *y, cudaStream_t s
             (u32)K.cols, K.nbk, K.blocked_tiles, K.num_tiles, hot, g_spmv_tma);
     }
     if (K.num_tiles > 1) {
-        k_spmv_fixup<<<cdiv(K.num_tiles - 1, 128), 128, 0, s>>>(K.voff, K.tile_row, K.carry, K.head, out, K.num_tiles, kBlkTile);
+        k_spmv_fixup<<<cdiv(K.num_tiles - 1, 128), 128, 0, s>>>(K.fix_row, K.fix_first, K.carry, K.head, out, K.num_tiles);
         if (launches) *launches += 1;
     }
     if (K.nslabs > 1) {
@@ -636,7 +633,7 @@ void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *l
         break;
     }
     if (A.num_tiles > 1) {
-        k_spmv_fixup<<<cdiv(A.num_tiles - 1, 128), 128, 0, s>>>(A.off, A.tile_row, A.carry, A.head, y, A.num_tiles, kSpmvTile);
+        k_spmv_fixup<<<cdiv(A.num_tiles - 1, 128), 128, 0, s>>>(A.fix_row, A.fix_first, A.carry, A.head, y, A.num_tiles);
         if (launches) *launches += 1;
     }
     LAS2_LAUNCH_CHECK();
