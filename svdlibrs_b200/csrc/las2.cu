@@ -409,6 +409,8 @@ struct Solver {
         res->diagnostics.singular_values = nsig;   // sic, :649
 
         const u64 mcols = M, ncols = N;
+        const bool trace = std::getenv("SVDLAS2_TRACE") != nullptr;
+        const double ta0 = wall();
         double *hU = (double *)(prefetched ? fut_m.get() : host_acquire(std::max<u64>(1, d * mcols) * sizeof(double)));
         double *hV = nullptr;
         try {
@@ -422,6 +424,9 @@ struct Solver {
         res->vt = tr ? hU : hV; res->vt_cols = tr ? mcols : ncols;
         res->s = hS;
         if (d == 0) return;
+        if (trace) fprintf(stderr, "[svdlas2] ritvec: host result buffers (%.2f GB) ready after %.3f s (prefetched=%d)\n",
+                           (double)(d * (mcols + ncols) * 8) / 1e9, wall() - ta0, (int)prefetched);
+        const double tc0 = wall();
 
         std::vector<u32> phys(d);
         for (u64 i = 0; i < d; i++) phys[i] = plan.column_of[accepted[nsig - 1 - i]];
@@ -432,6 +437,10 @@ struct Solver {
         DevBuf<double> V((size_t)d * ld);
         ritz_contract(Q.get(), ld, N, (u32)js, C.get(), (u32)d, V.get(), s, &prof.n_kernel_launches);
         LAS2_CUDA(cudaStreamSynchronize(s));
+        if (trace) fprintf(stderr, "[svdlas2] ritvec: contraction N=%llu js=%llu d=%llu in %.3f s (%.1f TFLOP/s)\n",
+                           (unsigned long long)N, (unsigned long long)js, (unsigned long long)d, wall() - tc0,
+                           2.0 * (double)N * (double)js * (double)d / (wall() - tc0) / 1e12);
+        const double tt0 = wall();
         zT.release();
         C.release();
         Q.release(); // the panel is no longer needed; make room for U
@@ -477,8 +486,10 @@ struct Solver {
         }
         LAS2_CUDA(cudaMemcpyAsync(hS, S.get(), d * sizeof(double), cudaMemcpyDeviceToHost, s));
         LAS2_CUDA(cudaStreamSynchronize(s));
+        if (trace) fprintf(stderr, "[svdlas2] ritvec: sigma/U tail (%llu SpMV) in %.3f s\n", (unsigned long long)d, wall() - tt0);
         const double td0 = wall();
         LAS2_CUDA(cudaStreamSynchronize(copy_stream));
+        if (trace) fprintf(stderr, "[svdlas2] ritvec: waited %.3f s more for the D2H stream\n", wall() - td0);
         prof.n_host_syncs += 2;
         prof.d2h_bytes += (d * ncols + d * mcols + d) * sizeof(double);
         prof.t_download = wall() - td0; // D2H time NOT hidden behind the sigma/U kernels
