@@ -9,7 +9,7 @@ A "step" is one whole svd_dim_seed(A, dims, seed=12345) of the named synthetic w
           (BASELINE.json: "svd_dim_seed time-to-SVD & opb matvecs/s"); time-to-SVD itself is in `time_to_svd_s`.
   value   operator already resident in HBM (svdlas2_operator_solve), CUDA-event time on the library's stream
   e2e     the reference-facing call svdlas2_csr/_csc with HOST buffers: upload + conversion + solve + D2H of ut/s/vt
-  roofline  the dominant kernel (k_spmv_stream, two launches per opb) timed live with CUDA events
+  roofline  the dominant kernel (k_spmv_chunk, two launches per opb) timed live with CUDA events
   cpu_baseline  the CPU oracle (oracle/, a restatement of the reference: the Rust crate cannot be built here),
           one thread like the reference, on a bounded sample (same matrix, `iterations` capped)
 --impl reference times that oracle alone with the same metric / config.
@@ -285,7 +285,7 @@ def run_ours(args):
         t = json.load(open(tp))
         if t.get("workload") == info["name"] and t.get("scale") == info["scale"]:
             traffic = t.get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_spmv_blocked<8> / k_spmv_stream (2 launches per opb: B then B')", "achieved": ach,
+    roofline = {"bound": "hbm", "kernel": "k_spmv_chunk (2 launches per opb: B then B')", "achieved": ach,
                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": tm["bytes_opb"] / 2, "ms_per_launch": tm["ms_per_opb"] / 2,
                 "spmv_b": {"GB/s": tm["bytes_spmv_b"] / tm["ms_spmv_b"] / 1e6, "ms": tm["ms_spmv_b"]},

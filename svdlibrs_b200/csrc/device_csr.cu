@@ -454,6 +454,13 @@ void build_fix_list(const u32 *off, const u32 *tile_row, u32 num_tiles, u32 tile
     st.launches++;
 }
 void build_blocked(DeviceCsr &X, cudaStream_t s, UploadStats &st); // blocked_csr.cu
+void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st); // chunk_spmv.cu
+
+// the SpMV-ready copies of a finished CSR matrix: the warp-chunk stream, else (opt-in / fallback) the older tile stream
+static void build_streams(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
+    build_chunk_stream(X, s, st);
+    if (!X.chk.active) build_blocked(X, s, st);
+}
 
 void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, const u64 *indices, const double *values,
                              cudaStream_t s, DeviceCsr &X, DeviceCsr &XT, UploadStats &st) {
@@ -481,8 +488,8 @@ void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, co
     stage.release();
     finish_csr(X, s, st);
     transpose_csr(X, XT, s, st);
-    build_blocked(X, s, st);
-    build_blocked(XT, s, st);
+    build_streams(X, s, st);
+    build_streams(XT, s, st);
 }
 
 void build_operator(const HostSparse &A, bool transposed, cudaStream_t s, DeviceCsr &B, DeviceCsr &BT, UploadStats &st) {
@@ -534,8 +541,8 @@ void build_operator(const HostSparse &A, bool transposed, cudaStream_t s, Device
         }
         finish_csr(X, s, st);
         transpose_csr(X, XT, s, st);
-        build_blocked(X, s, st);
-        build_blocked(XT, s, st);
+        build_streams(X, s, st);
+        build_streams(XT, s, st);
     } else {
         throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "unknown sparse format");
     }

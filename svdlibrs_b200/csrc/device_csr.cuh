@@ -46,9 +46,34 @@ struct BlockedCsr {
     u64 stream_bytes = 0;        // bytes one SpMV actually moves (for reporting)
 };
 
+// Warp-chunk stream (chunk_spmv.cu): the row-ordered non-zeros cut into chunks of 256, one warp per chunk.  A
+// chunk is 3072 contiguous bytes, fetched by ONE bulk copy: 4 x 32 x 16 B of values, then 2 x 32 x 16 B of
+// column indices, arranged so that six conflict-free 128-bit shared-memory reads hand lane l the 8 CONSECUTIVE
+// elements l*8 .. l*8+7 of the chunk.  Bit 31 of an index marks the first element of a row.
+constexpr u32 kChunkE = 8;                    // consecutive elements per lane
+constexpr u32 kChunkNnz = 32 * kChunkE;       // 256
+constexpr u32 kChunkBytes = kChunkNnz * 12;   // 3072
+constexpr u32 kChunkFlag = 0x80000000u;
+
+struct ChunkStream {
+    bool active = false;
+    u64 rows = 0, cols = 0;
+    u32 num_chunks = 0;
+    u32 nonempty_rows = 0;
+    bool has_empty_rows = false;
+    DevBuf<uint4> data;      // (num_chunks + 1) * 192
+    DevBuf<u32> chunk_row;   // num_chunks + 1: index (among the non-empty rows) of the first row that STARTS at or after
+                             // the chunk's first element; bit 31: some lane of the chunk holds two or more row starts
+    DevBuf<u32> rowmap;      // non-empty row index -> row (empty when every row is non-empty)
+    DevBuf<double> carry;    // num_chunks: sum of the piece that is still open at the chunk's end
+    DevBuf<double> head;     // num_chunks: sum of the piece that was open at the chunk's start, up to the first row start
+    DevBuf<u32> fix_row, fix_first; // num_chunks: row completed by chunk b's head (or ~0u) and the chunk it started in
+};
+
 struct DeviceCsr {
     u64 rows = 0, cols = 0, nnz = 0;
     BlockedCsr blk;
+    ChunkStream chk;
     DevBuf<u32> off;    // rows + 1 row offsets
     DevBuf<u32> idx;    // padded_nnz column indices (padding: index 0)
     DevBuf<double> val; // padded_nnz values        (padding: 0.0)

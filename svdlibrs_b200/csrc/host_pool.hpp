@@ -1,7 +1,9 @@
-// host_pool.hpp -- pinned host buffers for the SvdRec arrays (ut is d x rows(A) f64: 0.9 GB at cfg 2, 16 GB at
-// cfg 4).  D2H into pageable memory runs at ~2 GB/s (staging + first-touch page faults); into pinned memory it
-// runs at PCIe speed and overlaps with the kernels still computing later rows.  Pinning is expensive, so freed
-// result buffers are kept (up to SVDLAS2_HOST_CACHE_MB, default 4096 MiB) for the next call of the process.
+// host_pool.hpp -- DMA-able host buffers for the SvdRec arrays (ut is d x rows(A) f64: 0.9 GB at cfg 2, 16 GB at
+// cfg 4/5).  D2H into pageable memory is staged by the driver and pays first-touch page faults; into registered
+// memory it runs at PCIe speed and overlaps with the kernels still computing later rows.  Blocks are anonymous
+// huge-page mappings touched in parallel and then registered with CUDA (an order of magnitude faster than
+// cudaHostAlloc, see host_pool.cpp); freed result buffers are kept for the next call of the process, up to
+// SVDLAS2_HOST_CACHE_MB (default: the smaller of 32 GiB and 1/8 of the machine's RAM).
 #pragma once
 #include <cstddef>
 
@@ -12,6 +14,8 @@ namespace las2 {
 void *host_acquire(size_t bytes);
 // Gives a buffer obtained from host_acquire back (cached or freed). Pointers not from the pool are free()d.
 void host_release(void *p);
+// Largest result (bytes) worth allocating ahead of time on a helper thread: 1/4 of the machine's RAM.
+size_t host_prefetch_limit();
 // Frees every cached buffer (tests; process exit does it implicitly).
 void host_pool_trim();
 

@@ -85,7 +85,7 @@ struct Solver {
         w5.assign(iters + 2, 0.0);
         LAS2_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         const u64 want = dims * (M + N) * sizeof(double);
-        if (want <= ((u64)8 << 30)) { // only when the upper bound d <= dims is affordable
+        if (want <= host_prefetch_limit()) { // only when the upper bound d <= dims is affordable
             const int dev = op.device;
             const size_t bm = std::max<u64>(1, dims * M) * sizeof(double), bn = std::max<u64>(1, dims * N) * sizeof(double);
             fut_m = std::async(std::launch::async, [dev, bm] { cudaSetDevice(dev); return host_acquire(bm); });
@@ -493,6 +493,9 @@ struct Solver {
         prof.n_host_syncs += 2;
         prof.d2h_bytes += (d * ncols + d * mcols + d) * sizeof(double);
         prof.t_download = wall() - td0; // D2H time NOT hidden behind the sigma/U kernels
+        const double tf0 = wall();
+        U.release(); V.release(); S.release(); nrm2.release();
+        if (trace) fprintf(stderr, "[svdlas2] ritvec: device buffers released in %.3f s\n", wall() - tf0);
     }
 };
 

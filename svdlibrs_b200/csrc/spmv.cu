@@ -594,8 +594,14 @@ void spmv_blocked(const DeviceCsr &A, const double *x, double *y, cudaStream_t s
 }
 } // namespace
 
+void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches); // chunk_spmv.cu
+
 void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
     if (A.rows == 0) return;
+    if (A.chk.active && (g_spmv_variant < 0 || g_spmv_variant == 5)) {
+        spmv_chunk(A, x, y, s, launches);
+        return;
+    }
     if (A.blk.active && (g_spmv_variant < 0 || g_spmv_variant == 4)) {
         spmv_blocked(A, x, y, s, launches);
         return;

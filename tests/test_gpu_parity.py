@@ -132,13 +132,18 @@ def test_coo_duplicates_are_summed(las2, oracle):
     assert_svd_parity(got, ref)
 
 
-def test_spmv_ragged_rows(las2, oracle):
-    """rows of length 0, 1 and > one nnz-tile, leading / trailing empty rows, tile-straddling rows"""
+@pytest.mark.parametrize("spmv", ["", "chunk"])
+def test_spmv_ragged_rows(las2, oracle, spmv, monkeypatch):
+    """rows of length 0, 1 and > one nnz-tile, leading / trailing empty rows, tile-straddling rows; with the
+    small-matrix kernel (default at this size) and with the warp-chunk stream forced (rows shorter than a lane's 8
+    elements, rows spanning > 32 chunks, empty rows -> row map)"""
+    monkeypatch.setenv("SVDLAS2_SPMV", spmv)
     rng = np.random.default_rng(11)
     nrows, ncols = 700, 9000
     lens = np.zeros(nrows, dtype=int)
     lens[5] = 9000; lens[6] = 1; lens[7] = 5000; lens[300:310] = 33; lens[310:340] = 32; lens[400] = 4097
     lens[500:650] = rng.integers(0, 60, 150)
+    lens[650:660] = 8; lens[660] = 256; lens[661] = 257; lens[662] = 255; lens[663:690] = rng.integers(0, 4, 27)
     rows, cols = [], []
     for i, l in enumerate(lens):
         c = np.sort(rng.choice(ncols, size=l, replace=False))
@@ -215,16 +220,19 @@ def test_iterations_and_kappa_parameters(las2, oracle):
     assert_svd_parity(got, ref)
 
 
-@pytest.mark.parametrize("variant,hot", [(0, -1), (1, -1), (2, -1), (3, 0), (3, 5), (3, 1000), (3, -1), (4, -1), (5, -1), (5, 0), (5, 7)])
+@pytest.mark.parametrize("variant,hot", [(0, -1), (1, -1), (2, -1), (3, 0), (3, 5), (3, 1000), (3, -1), (4, -1), (5, -1), (5, 0), (5, 7),
+                                         (6, -1), (6, 0), (6, 7), (6, 4096), (6, 8192)])
 def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
-    """all SpMV kernels (one-CTA-per-tile with 256/128/512 threads, persistent hot-prefix kernel with several
-    shared-memory prefix sizes) on ragged + power-law inputs, both orientations"""
+    """all SpMV kernels (warp-chunk stream with several shared-memory prefix sizes, one-CTA-per-tile with 256/128/512
+    threads, persistent hot-prefix kernel, blocked/interleaved tile streams) on ragged + power-law inputs, both
+    orientations"""
     import os
     from svdlibrs_b200 import synthetic
-    # the column-blocked / interleaved copies are built on request: 4 = slabs where they pay, 5 = no slabs
+    # test variant -> (library variant, formats built at upload): 4 = slabs where they pay, 5 = tile stream without
+    # slabs, 6 = the warp-chunk stream (the default of large matrices, forced here at test size)
+    os.environ["SVDLAS2_SPMV"] = "chunk" if variant == 6 else "tile"
     os.environ["SVDLAS2_BLOCKED"] = {4: "1", 5: "2"}.get(variant, "0")
-    if variant == 5:
-        variant = 4
+    variant = {5: 4, 6: 5}.get(variant, variant)
     rng = np.random.default_rng(21)
     mats = [synthetic.make("cfg2", scale=0.01)[0],
             sp.random(3000, 5000, density=0.004, format="csr", random_state=rng)]
@@ -244,7 +252,8 @@ def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
             finally:
                 op.set("spmv_variant", -1)
                 op.set("spmv_hot", -1)
-                os.environ["SVDLAS2_BLOCKED"] = "0"
+                os.environ.pop("SVDLAS2_BLOCKED", None)
+                os.environ.pop("SVDLAS2_SPMV", None)
 
 
 def test_cfg2_full_size_invariants(las2):
