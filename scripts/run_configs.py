@@ -17,9 +17,11 @@ for spec in sys.argv[1:]:
     gen = time.time() - t0
     rec = dict(config=name, scale=scale, shape=list(A.shape), nnz=int(A.nnz), fmt=A.format, dims=int(dims), gen_s=round(gen, 1))
     try:
+        las2.svd_dim_seed(A, min(dims, 10), 12345, ) if False else None
         t0 = time.perf_counter()
         r = las2.svd_dim_seed(A, dims, 12345)
         e2e = time.perf_counter() - t0
+        pe = dict(r.profile)
         with las2.Operator(A) as op:
             t0 = time.perf_counter(); r2 = op.solve(dims, random_seed=12345); res = time.perf_counter() - t0
             tm = op.time_opb(reps=10)
@@ -33,6 +35,7 @@ for spec in sys.argv[1:]:
                    sigma_last=float(r.s[-1]) if r.d else None, deterministic=bool(r == r2), ortho_defect16=ortho, resid0=resid,
                    ms_per_opb=round(tm["ms_per_opb"], 4), opb_GBs=round(tm["bytes_opb"] / tm["ms_per_opb"] / 1e6, 1),
                    phases={k: round(p[k], 4) for k in ("t_upload", "t_lanczos", "t_sync_wait", "t_ritvec", "t_imtql2", "t_download")},
+                   e2e_phases={k: round(pe[k], 4) for k in ("t_upload", "t_lanczos", "t_ritvec", "t_imtql2", "t_total")},
                    purge_fired=int(p["n_purge_fired"]), purge_vectors=int(p["n_purge_vectors"]), launches=int(p["n_kernel_launches"]))
     except las2.SvdLibError as e:
         rec.update(error=str(e))

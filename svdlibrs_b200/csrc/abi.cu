@@ -267,6 +267,8 @@ int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value)
     if (!std::strcmp(knob, "spmv_hot")) { g_spmv_hot_entries = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_tma")) { g_spmv_tma = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_smem_pad_kb")) { g_chunk_smem_pad_kb = (int)value; return SVDLAS2_OK; }
+    if (!std::strcmp(knob, "spmv_pdl")) { g_chunk_pdl = (int)value; return SVDLAS2_OK; }
+    if (!std::strcmp(knob, "spmv_shape")) { g_chunk_shape = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_carveout")) { g_chunk_carveout_pct = (int)value; return SVDLAS2_OK; }
     return fail(SVDLAS2_ERR_INVALID_ARGUMENT, std::string("unknown knob ") + knob);
 }

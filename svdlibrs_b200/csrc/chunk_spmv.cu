@@ -19,24 +19,34 @@
 //     k_chunk_fixup completes those rows in chunk order.  Every order is fixed by the data layout: deterministic.
 //   * Chunks in which some lane holds two or more row starts (rows shorter than 8) take a branchy variant of the
 //     per-lane step (marked at upload in bit 31 of chunk_row[]); everything else is shared.
+//   * Slab mode (MODE 2; chosen at upload when a (16384-column block, row) piece holds >= 4 entries on average): the
+//     stream is ordered (slab, row, column) with local column indices, each CTA takes a contiguous range of chunks
+//     and keeps the slab's 128 KB slice of x in shared memory, so EVERY gather is an ld.shared (~0.33 wavefronts
+//     instead of one L1 line; profiles/r1f_spmv_ncu_summary.md shows the L1TEX pipe, not HBM, bounding MODE 0/1).
+//     The rows of the stream are then the non-empty (slab, row) pieces; partial sums are written by running piece
+//     number (dense, coalesced) and k_slab_reduce adds the pieces of a row in slab order.
 //
 // Algorithmic bytes per launch: 12*Z + 4*(R+1) + 8*C + 8*R.
 #include <algorithm>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "spmv.cuh"
 
 namespace las2 {
 
 void exclusive_scan_u32(u32 *data, u64 n, cudaStream_t s, UploadStats &st); // device_csr.cu
+void expand_row_ids(const u32 *off, u32 rows, u64 nnz, u32 *rowid, cudaStream_t s, UploadStats &st);
 
 namespace {
 
-constexpr int kChunkWarps = 16;
-constexpr int kChunkThreads = kChunkWarps * 32;
+// launch shapes: (warps per CTA, stages per warp).  Both fill 96 KB of shared memory with stages.  16 x 2 hides the
+// bulk-copy latency inside each warp; 32 x 1 doubles the warps that hide each other's ALU / shuffle latencies (the
+// slab mode is latency-bound: 41 % issue-active with 4 warps per scheduler, profiles/r1g).
+constexpr int kChunkStageBytesTotal = 32 * kChunkBytes;
 constexpr u32 kChunkHotMax = 8192; // doubles of x kept in shared memory at most (64 KB)
-constexpr u32 kChunkHotDefault = 4096;
+constexpr u32 kChunkHotDefault = 8192; // cfg 2, B: 0.116 ms with 8192 entries, 0.122 ms with 4096
 
 // ------------------------------------------------------------------------------------------------ build
 
@@ -125,6 +135,104 @@ __global__ void k_chunk_flags(const u32 *__restrict__ cstart, u32 nc, uint4 *__r
     }
 }
 
+// ---- slab mode ----
+
+// cnt[slab * rows + row] += 1 for every non-zero (integer atomics: the result does not depend on the order)
+__global__ void k_piece_count(const u32 *__restrict__ idx, const u32 *__restrict__ rowid, u64 nnz, u64 rows,
+                              u32 *__restrict__ cnt) {
+    u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; k < nnz; k += stride) atomicAdd(&cnt[(u64)(idx[k] / kSlabWidth) * rows + rowid[k]], 1u);
+}
+
+// ne[v] = cnt[v] > 0 (ne has one more slot, set to 0, so that the scan leaves the total there)
+__global__ void k_piece_nonempty(const u32 *__restrict__ cnt, u64 npieces, u32 *__restrict__ ne) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; v <= npieces; v += stride) ne[v] = (v < npieces && cnt[v] > 0) ? 1u : 0u;
+}
+
+// cstart[piece_id[v]] = padded stream position of piece v; cstart[total] = sentinel
+__global__ void k_piece_starts(const u32 *__restrict__ pos, const u32 *__restrict__ piece_id, const u32 *__restrict__ shift,
+                               u64 npieces, u64 rows, u32 sentinel, u32 *__restrict__ cstart) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; v <= npieces; v += stride) {
+        if (v == npieces) { cstart[piece_id[npieces]] = sentinel; continue; }
+        if (piece_id[v + 1] > piece_id[v]) cstart[piece_id[v]] = pos[v] + shift[v / rows];
+    }
+}
+
+// ranked scatter into the (slab, row, column) order: inside a row the entries of one slab are contiguous (columns
+// ascend), so the rank of entry k inside its piece is k minus the position of the piece's first entry in the row
+__global__ void k_slab_scatter(const u32 *__restrict__ off, const u32 *__restrict__ idx, const double *__restrict__ val,
+                               const u32 *__restrict__ rowid, u64 nnz, u64 rows, const u32 *__restrict__ pos,
+                               const u32 *__restrict__ shift, uint4 *__restrict__ data) {
+    double *dv = reinterpret_cast<double *>(data);
+    u32 *di = reinterpret_cast<u32 *>(data);
+    u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; k < nnz; k += stride) {
+        const u32 c = idx[k], r = rowid[k];
+        const u32 sl = c / kSlabWidth;
+        const u32 first_col = sl * kSlabWidth;
+        u32 lo = off[r], hi = (u32)k; // lower_bound of first_col in idx[off[r] .. k]
+        while (lo < hi) {
+            const u32 mid = lo + ((hi - lo) >> 1);
+            if (idx[mid] < first_col) lo = mid + 1; else hi = mid;
+        }
+        const u64 e = (u64)pos[(u64)sl * rows + r] + shift[sl] + ((u32)k - lo);
+        dv[chunk_val_slot(e)] = val[k];
+        di[chunk_idx_slot(e)] = c - first_col;
+    }
+}
+
+// y[r] = sum of the partials of the pieces (slab, r).  Eight lanes share a row: lane q sums slabs q, q+8, q+16, ... in
+// ascending order (piece numbers first -- static, fetched before the grid dependency resolves -- then the partials,
+// independent loads), and a fixed three-step shuffle tree adds the eight sums.  Consecutive groups take consecutive
+// rows, so for a fixed slab the piece numbers and partials of a warp's four rows are adjacent in memory.
+constexpr int kReduceLanes = 8;
+constexpr int kReduceMaxPerLane = 16; // slabs per lane held in registers; more slabs fall back to the loop below
+__global__ void __launch_bounds__(256)
+k_slab_reduce(const u32 *__restrict__ piece_id, const double *__restrict__ part, u64 rows, u32 nslabs,
+              double *__restrict__ y) {
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 r = gid / kReduceLanes;
+    const u32 q = (u32)(gid % kReduceLanes);
+    const bool live = r < rows;
+    double s = 0.0;
+    if (nslabs <= kReduceLanes * kReduceMaxPerLane) {
+        u32 id[kReduceMaxPerLane];
+        bool on[kReduceMaxPerLane];
+#pragma unroll
+        for (int j = 0; j < kReduceMaxPerLane; j++) {
+            const u32 b = q + j * kReduceLanes;
+            on[j] = false;
+            if (live && b < nslabs) {
+                const u64 v = (u64)b * rows + r;
+                id[j] = piece_id[v];
+                on[j] = piece_id[v + 1] > id[j];
+            }
+        }
+        cudaGridDependencySynchronize();
+        double p[kReduceMaxPerLane];
+#pragma unroll
+        for (int j = 0; j < kReduceMaxPerLane; j++) p[j] = on[j] ? part[id[j]] : 0.0;
+#pragma unroll
+        for (int j = 0; j < kReduceMaxPerLane; j++) s += p[j];
+    } else {
+        cudaGridDependencySynchronize();
+        for (u32 b = q; live && b < nslabs; b += kReduceLanes) {
+            const u64 v = (u64)b * rows + r;
+            const u32 id = piece_id[v];
+            if (piece_id[v + 1] > id) s += part[id];
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < kReduceLanes; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (live && q == 0) y[r] = s;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 
 __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
@@ -144,57 +252,36 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity) {
 }
 __device__ __forceinline__ double u2d(u32 lo, u32 hi) { return __hiloint2double((int)hi, (int)lo); }
 
-constexpr size_t kChunkBarBytes = 256; // 16 warps x 2 mbarriers
-size_t chunk_smem_bytes(u32 hot) { return kChunkBarBytes + (size_t)kChunkWarps * 2 * kChunkBytes + (size_t)hot * sizeof(double); }
+constexpr size_t kChunkBarBytes = 256; // up to 32 mbarriers
+size_t chunk_smem_bytes(u32 hot) { return kChunkBarBytes + (size_t)kChunkStageBytesTotal + (size_t)hot * sizeof(double); }
 
-template <bool HOT>
-__global__ void __launch_bounds__(kChunkThreads, 1)
-k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, const u32 *__restrict__ rowmap,
-             const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry,
-             double *__restrict__ head, u32 num_chunks, u32 hot) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);
-    unsigned char *stages = smem_raw + kChunkBarBytes;
-    const double *xs = reinterpret_cast<const double *>(stages + (size_t)kChunkWarps * 2 * kChunkBytes);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u64 pol_stream = l2_policy_evict_first();
-    const u64 pol_keep = l2_policy_evict_last();
-    unsigned long long *bar = bars + warp * 2;
-    unsigned char *stage = stages + (size_t)warp * 2 * kChunkBytes;
-
-    const u32 total_warps = gridDim.x * kChunkWarps;
-    u32 c = blockIdx.x * kChunkWarps + warp;
+// One warp's walk over the chunks first, first + step, ... < stop.  MODE 0: every gather through L1; 1: columns below
+// `hot` from the shared-memory prefix xs, the rest through L1; 2: every gather from the shared-memory slice xs.
+template <int MODE, int STAGES>
+__device__ __forceinline__ void chunk_walk(u32 first, u32 stop, u32 step, int lane, unsigned long long *bar,
+                                           unsigned char *stage, u32 &phases, const double *xs, u32 hot,
+                                           const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row,
+                                           const u32 *__restrict__ rowmap, const double *__restrict__ x,
+                                           double *__restrict__ y, double *__restrict__ carry, double *__restrict__ head,
+                                           u64 pol_stream, u64 pol_keep) {
+    if (first >= stop) return;
+    u32 c = first;
     if (lane == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (c < num_chunks) {
-            mbar_expect_tx(&bar[0], kChunkBytes);
-            bulk_load(stage, data + (u64)c * (kChunkBytes / 16), kChunkBytes, &bar[0], pol_stream);
-        }
-        if (c + total_warps < num_chunks) {
-            mbar_expect_tx(&bar[1], kChunkBytes);
-            bulk_load(stage + kChunkBytes, data + (u64)(c + total_warps) * (kChunkBytes / 16), kChunkBytes, &bar[1], pol_stream);
+#pragma unroll
+        for (int j = 0; j < STAGES; j++) {
+            if (c + j * step < stop) {
+                mbar_expect_tx(&bar[j], kChunkBytes);
+                bulk_load(stage + j * kChunkBytes, data + (u64)(c + j * step) * (kChunkBytes / 16), kChunkBytes, &bar[j], pol_stream);
+            }
         }
     }
-    if (HOT) {
-        double *xw = const_cast<double *>(xs);
-        for (u32 i = threadIdx.x; i < hot; i += kChunkThreads) xw[i] = ld_gather_f64(x + i, pol_keep);
-        __syncthreads(); // the only block-wide barrier of the kernel
-    } else {
-        __syncwarp();
-    }
-
     const u32 lt_mask = (1u << lane) - 1u;
-    u32 phases = 0;
-    // the chunk descriptor is fetched one iteration ahead: consecutive chunks of a warp are total_warps apart, so
-    // every such load is a DRAM-latency miss (it was the top stall of the first version of this kernel)
-    u32 cr_next = c < num_chunks ? chunk_row[c] : 0u;
-    for (u32 it = 0; c < num_chunks; c += total_warps, it++) {
-        const u32 sidx = it & 1u;
+    // the chunk descriptor is fetched one iteration ahead (consecutive chunks of a warp are far apart in memory)
+    u32 cr_next = chunk_row[c];
+    for (u32 it = 0; c < stop; c += step, it++) {
+        const u32 sidx = STAGES == 1 ? 0u : (it & 1u);
         const u32 cr = cr_next;
-        if (c + total_warps < num_chunks) cr_next = chunk_row[c + total_warps];
+        if (c + step < stop) cr_next = chunk_row[c + step];
         mbar_wait(&bar[sidx], (phases >> sidx) & 1u);
         phases ^= 1u << sidx;
         const uint4 *st = reinterpret_cast<const uint4 *>(stage + sidx * kChunkBytes);
@@ -213,7 +300,9 @@ k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, 
 #pragma unroll
         for (int k = 0; k < (int)kChunkE; k++) {
             const u32 col = ci[k] & ~kChunkFlag;
-            if (HOT) {
+            if (MODE == 2) {
+                xv[k] = xs[col];
+            } else if (MODE == 1) {
                 if (col < hot) xv[k] = xs[col];
                 else xv[k] = ld_gather_f64(x + col, pol_keep);
             } else {
@@ -239,13 +328,10 @@ k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, 
             u32 nf = 0;
 #pragma unroll
             for (int k = 0; k < (int)kChunkE; k++) nf += ci[k] >> 31;
-            u32 incl = nf;
+            // exclusive prefix of nf (0 .. 8) over the lanes, bit-sliced: four ballots instead of a five-step shuffle scan
+            base = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            base = incl - nf;
+            for (int b = 0; b < 4; b++) base += (u32)__popc(__ballot_sync(0xffffffffu, (nf >> b) & 1u) & lt_mask) << b;
             u32 j = 0;
 #pragma unroll
             for (int k = 0; k < (int)kChunkE; k++) {
@@ -266,6 +352,13 @@ k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, 
 
         // ---- stitch the lanes: segmented inclusive scan of the pieces open at each lane's end ----
         const u32 mask = __ballot_sync(0xffffffffu, seen);
+        // Every lane's reads of the stage have completed: the multiply-adds above consumed all six loaded vectors and
+        // the ballot is issued for the whole warp only once they have.  Refill the slot for the chunk STAGES ahead.
+        if (lane == 0 && c + STAGES * step < stop) {
+            mbar_expect_tx(&bar[sidx], kChunkBytes);
+            bulk_load(stage + sidx * kChunkBytes, data + (u64)(c + STAGES * step) * (kChunkBytes / 16), kChunkBytes, &bar[sidx],
+                      pol_stream);
+        }
         if (!(cr & kChunkFlag)) base = __popc(mask & lt_mask);
         double xsum = seen ? tsum : hsum;
         const u32 le = mask & (lt_mask | (1u << lane));
@@ -277,13 +370,6 @@ k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, 
         }
         double cin = __shfl_up_sync(0xffffffffu, xsum, 1);
         if (lane == 0) cin = 0.0;
-
-        // every lane's stage reads have long completed (their values fed the shuffles above): refill the slot
-        if (lane == 0 && c + 2 * total_warps < num_chunks) {
-            mbar_expect_tx(&bar[sidx], kChunkBytes);
-            bulk_load(stage + sidx * kChunkBytes, data + (u64)(c + 2 * total_warps) * (kChunkBytes / 16), kChunkBytes,
-                      &bar[sidx], pol_stream);
-        }
 
         // ---- emission: a lane with a row start closes the piece that was open before it ----
         if (seen) {
@@ -299,22 +385,84 @@ k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, 
     }
 }
 
-// Rows that cross chunk boundaries: y[row] = carry[first] + ... + carry[b-1] + head[b].  One lane per chunk; spans of
-// more than 32 chunks (rows with > 8192 entries) are summed by the whole warp: lane-strided partial sums in chunk
-// order, then a fixed shuffle tree.
+template <int MODE, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, const u32 *__restrict__ rowmap,
+             const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry,
+             double *__restrict__ head, u32 num_chunks, u32 hot, const u32 *__restrict__ slab_chunk_start, u32 nslabs,
+             u32 cols) {
+    cudaTriggerProgrammaticLaunchCompletion(); // the fix-up kernel may take over SMs as CTAs of this grid retire
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned char *stages = smem_raw + kChunkBarBytes;
+    static_assert(WARPS * STAGES * kChunkBytes == kChunkStageBytesTotal, "stages fill 96 KB");
+    constexpr int kChunkWarps = WARPS, kChunkThreads = WARPS * 32;
+    double *xs = reinterpret_cast<double *>(stages + (size_t)kChunkStageBytesTotal);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u64 pol_stream = l2_policy_evict_first();
+    const u64 pol_keep = l2_policy_evict_last();
+    unsigned long long *bar = bars + warp * STAGES;
+    unsigned char *stage = stages + (size_t)warp * STAGES * kChunkBytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < STAGES; j++) mbar_init(&bar[j], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    u32 phases = 0;
+
+    // Programmatic dependent launch: up to here only this kernel's own shared memory was touched; x (written by the
+    // kernel before this one) is read and y / carry / head are written only after the preceding grid has completed.
+    cudaGridDependencySynchronize();
+
+    if (MODE == 2) {
+        // contiguous share of the chunks: one or two slabs per CTA, i.e. one or two loads of a 128 KB slice of x
+        const u32 lo = (u32)(((u64)num_chunks * blockIdx.x) / gridDim.x);
+        const u32 hi = (u32)(((u64)num_chunks * (blockIdx.x + 1)) / gridDim.x);
+        u32 sl = 0;
+        for (u32 cur = lo; cur < hi;) {
+            while (sl + 1 < nslabs && slab_chunk_start[sl + 1] <= cur) sl++;
+            const u32 stop = min(hi, slab_chunk_start[sl + 1]);
+            __syncthreads(); // every warp is done with the previous slice
+            const u32 col0 = sl * kSlabWidth;
+            for (u32 i = threadIdx.x; i < kSlabWidth; i += kChunkThreads)
+                xs[i] = (col0 + i < cols) ? ld_gather_f64(x + col0 + i, pol_keep) : 0.0;
+            __syncthreads();
+            chunk_walk<2, STAGES>(cur + warp, stop, kChunkWarps, lane, bar, stage, phases, xs, 0u, data, chunk_row, rowmap, x, y,
+                          carry, head, pol_stream, pol_keep);
+            cur = stop;
+        }
+    } else {
+        if (MODE == 1) {
+            for (u32 i = threadIdx.x; i < hot; i += kChunkThreads) xs[i] = ld_gather_f64(x + i, pol_keep);
+            __syncthreads(); // the only block-wide barrier of this mode
+        }
+        chunk_walk<MODE, STAGES>(blockIdx.x * kChunkWarps + warp, num_chunks, gridDim.x * kChunkWarps, lane, bar, stage, phases, xs,
+                         hot, data, chunk_row, rowmap, x, y, carry, head, pol_stream, pol_keep);
+    }
+}
+
+// Rows that cross chunk boundaries: y[row] = carry[first] + ... + carry[b-1] + head[b].  One lane per chunk; the common
+// span of one chunk needs no loop (all loads issued together); spans of more than 32 chunks (rows with > 8192 entries)
+// are summed by the whole warp: lane-strided partial sums in chunk order, then a fixed shuffle tree.  Launched with
+// programmatic stream serialisation: the (static) fix-up lists are fetched while the SpMV kernel drains.
 __global__ void __launch_bounds__(256)
 k_chunk_fixup(const u32 *__restrict__ fix_row, const u32 *__restrict__ fix_first, const double *__restrict__ carry,
               const double *__restrict__ head, double *__restrict__ y, u32 num_chunks) {
+    cudaTriggerProgrammaticLaunchCompletion(); // dependents may be scheduled as soon as SM resources free up
     const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     u32 row = 0xffffffffu, first = 0;
     if (b < num_chunks) { row = fix_row[b]; first = fix_first[b]; }
+    cudaGridDependencySynchronize();
     const bool mine = row != 0xffffffffu;
     const bool is_long = mine && (b - first > 32u);
     if (mine && !is_long) {
-        double s = 0.0;
-        for (u32 t = first; t < b; t++) s += carry[t];
-        y[row] = s + head[b];
+        const double h = head[b];
+        double s = carry[first];
+        for (u32 t = first + 1; t < b; t++) s += carry[t];
+        y[row] = s + h;
     }
     u32 todo = __ballot_sync(0xffffffffu, is_long);
     while (todo) {
@@ -329,32 +477,130 @@ k_chunk_fixup(const u32 *__restrict__ fix_row, const u32 *__restrict__ fix_first
     }
 }
 
-int g_chunk_carve_hot = -2, g_chunk_carve_cold = -2; // carve-out currently set on the two instantiations
+int g_chunk_carve[6] = {-2, -2, -2, -2, -2, -2}; // carve-out currently set on each instantiation
 
 } // namespace
 
 int g_chunk_smem_pad_kb = 0;  // tuning knob "spmv_smem_pad_kb": extra (unused) dynamic shared memory
+int g_chunk_pdl = 1;           // tuning knob "spmv_pdl": programmatic dependent launch of the SpMV kernel chain
+int g_chunk_shape = 32;        // tuning knob "spmv_shape": 32 = 32 warps x 1 stage, 16 = 16 warps x 2 stages
 int g_chunk_carveout_pct = -1; // tuning knob "spmv_carveout": shared-memory carve-out in percent of 228 KB (-1: exact fit)
 
 
 
-// Builds X.chk from the natural CSR arrays of X (device-side, deterministic).
-void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
-    ChunkStream &K = X.chk;
-    K = ChunkStream();
-    // SVDLAS2_SPMV: unset = this format for matrices large enough to fill the persistent kernel; "chunk" = always;
-    // anything else (e.g. "tile", "blocked") = never (the older kernels stay reachable for comparison).
-    const char *want = std::getenv("SVDLAS2_SPMV");
-    const bool force = want && std::string(want) == "chunk";
-    if (want && want[0] && !force) return;
-    if (X.nnz == 0 || X.rows == 0) return;
-    if (!force && X.nnz < (u64)8 * kNumSMs * kSpmvTile) return;
-    if (X.cols >= kChunkFlag || X.nnz + 2 * (u64)kChunkNnz >= ((u64)1 << 32)) return;
+namespace {
 
+// Launch with programmatic stream serialisation: the kernel may start while its predecessor in the stream drains; it
+// must call cudaGridDependencySynchronize() before touching anything the predecessor wrote (or still reads).
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_chunk_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LAS2_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
+unsigned grid_for(u64 n, unsigned per) {
+    unsigned g = cdiv(n, per);
+    return std::max(1u, std::min<unsigned>(g, kNumSMs * 32));
+}
+
+// chunk table, fix-up lists, row-start bits and carry buffers for a stream whose rows start at cstart[0 .. nc-1]
+// (ascending positions in the padded stream; cstart[nc] = the sentinel right behind the last real element)
+void finalize_chunks(ChunkStream &K, const u32 *cstart, const u32 *rowmap, u32 nc, u32 num_chunks, cudaStream_t s,
+                     UploadStats &st) {
+    K.chunk_row.alloc((size_t)num_chunks + 1);
+    k_chunk_rows<<<cdiv((u64)num_chunks + 1, 256), 256, 0, s>>>(cstart, nc, num_chunks, K.chunk_row);
+    LAS2_LAUNCH_CHECK();
+    K.fix_row.alloc(num_chunks);
+    K.fix_first.alloc(num_chunks);
+    k_chunk_fix_list<<<cdiv(num_chunks, 256), 256, 0, s>>>(cstart, rowmap, K.chunk_row, num_chunks, K.fix_row, K.fix_first);
+    LAS2_LAUNCH_CHECK();
+    k_chunk_flags<<<grid_for((u64)nc + 1, 256), 256, 0, s>>>(cstart, nc, K.data, K.chunk_row);
+    LAS2_LAUNCH_CHECK();
+    st.launches += 3;
+    K.carry.alloc(num_chunks);
+    K.head.alloc(num_chunks);
+    LAS2_CUDA(cudaMemsetAsync(K.carry.get(), 0, num_chunks * sizeof(double), s));
+    LAS2_CUDA(cudaMemsetAsync(K.head.get(), 0, num_chunks * sizeof(double), s));
+    K.num_chunks = num_chunks;
+}
+
+// Slab mode.  Returns false (leaving K untouched apart from scratch) when the matrix is too sparse per piece.
+bool build_slab_stream(DeviceCsr &X, ChunkStream &K, bool force, cudaStream_t s, UploadStats &st) {
+    const u64 rows = X.rows, nnz = X.nnz;
+    const u32 nslabs = cdiv(X.cols, kSlabWidth);
+    const u64 npieces = (u64)nslabs * rows;
+    if (nslabs < 2 || npieces + 1 >= ((u64)1 << 28)) return false;
+    const double min_per_piece = 4.0;
+
+    DevBuf<u32> rowid(nnz);
+    {
+        // rowid[k] = row of entry k (upper_bound over the offsets)
+        expand_row_ids(X.off, (u32)rows, nnz, rowid, s, st);
+    }
+    DevBuf<u32> pos(npieces + 1);
+    LAS2_CUDA(cudaMemsetAsync(pos.get(), 0, (npieces + 1) * sizeof(u32), s));
+    k_piece_count<<<grid_for(nnz, 256 * 4), 256, 0, s>>>(X.idx, rowid, nnz, rows, pos);
+    LAS2_LAUNCH_CHECK();
+    K.piece_id.alloc(npieces + 1);
+    k_piece_nonempty<<<grid_for(npieces + 1, 256 * 4), 256, 0, s>>>(pos, npieces, K.piece_id);
+    LAS2_LAUNCH_CHECK();
+    st.launches += 2;
+    exclusive_scan_u32(K.piece_id, npieces + 1, s, st);
+    u32 nc = 0;
+    LAS2_CUDA(cudaMemcpyAsync(&nc, K.piece_id.get() + npieces, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    LAS2_CUDA(cudaStreamSynchronize(s));
+    if (nc == 0 || (!force && (double)nnz < min_per_piece * (double)nc)) { K.piece_id.release(); return false; }
+
+    // positions: entries per piece -> exclusive scan; every slab then starts on a chunk boundary
+    exclusive_scan_u32(pos, npieces + 1, s, st);
+    std::vector<u32> starts(nslabs + 1);
+    LAS2_CUDA(cudaMemcpy2DAsync(starts.data(), sizeof(u32), pos.get(), rows * sizeof(u32), sizeof(u32), nslabs + 1,
+                                cudaMemcpyDeviceToHost, s));
+    LAS2_CUDA(cudaStreamSynchronize(s));
+    std::vector<u32> shift(nslabs), chunk_start(nslabs + 1);
+    u64 p = 0, sentinel = 0;
+    for (u32 i = 0; i < nslabs; i++) {
+        shift[i] = (u32)(p - starts[i]);
+        chunk_start[i] = (u32)(p / kChunkNnz);
+        sentinel = p + (starts[i + 1] - starts[i]);
+        p = (sentinel + kChunkNnz - 1) / kChunkNnz * kChunkNnz;
+    }
+    if (sentinel + 2 * (u64)kChunkNnz >= ((u64)1 << 32)) { K.piece_id.release(); return false; }
+    const u32 num_chunks = (u32)(sentinel / kChunkNnz) + 1; // the sentinel's chunk belongs to the last slab
+    chunk_start[nslabs] = num_chunks;
+    DevBuf<u32> dshift(nslabs);
+    LAS2_CUDA(cudaMemcpyAsync(dshift.get(), shift.data(), nslabs * sizeof(u32), cudaMemcpyHostToDevice, s));
+    K.slab_chunk_start.alloc(nslabs + 1);
+    LAS2_CUDA(cudaMemcpyAsync(K.slab_chunk_start.get(), chunk_start.data(), (nslabs + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
+
+    DevBuf<u32> cstart((size_t)nc + 1);
+    k_piece_starts<<<grid_for(npieces + 1, 256 * 4), 256, 0, s>>>(pos, K.piece_id, dshift, npieces, rows, (u32)sentinel, cstart);
+    LAS2_LAUNCH_CHECK();
+    K.data.alloc(((size_t)num_chunks + 1) * (kChunkBytes / 16));
+    LAS2_CUDA(cudaMemsetAsync(K.data.get(), 0, ((size_t)num_chunks + 1) * kChunkBytes, s)); // padding: value 0, column 0
+    k_slab_scatter<<<grid_for(nnz, 256 * 2), 256, 0, s>>>(X.off, X.idx, X.val, rowid, nnz, rows, pos, dshift, K.data);
+    LAS2_LAUNCH_CHECK();
+    st.launches += 2;
+    finalize_chunks(K, cstart, nullptr, nc, num_chunks, s, st);
+    K.part.alloc(nc);
+    LAS2_CUDA(cudaMemsetAsync(K.part.get(), 0, (size_t)nc * sizeof(double), s));
+    LAS2_CUDA(cudaStreamSynchronize(s)); // scratch and host vectors go out of scope
+    K.slabs = true;
+    K.nslabs = nslabs;
+    K.nonempty_rows = nc;
+    K.stream_bytes = (u64)num_chunks * kChunkBytes + 4 * (u64)num_chunks + 16 * (u64)nc + 4 * (npieces + 1) + 8 * X.cols * 2 + 8 * rows;
+    return true;
+}
+
+void build_plain_stream(DeviceCsr &X, ChunkStream &K, cudaStream_t s, UploadStats &st) {
     const u32 rows = (u32)X.rows, nnz = (u32)X.nnz;
     const u32 num_chunks = nnz / kChunkNnz + 1; // always room for the sentinel row start at element nnz
     const u64 padded = (u64)num_chunks * kChunkNnz;
-    auto grid_for = [](u64 n, unsigned per) { unsigned g = cdiv(n, per); return std::max(1u, std::min<unsigned>(g, kNumSMs * 32)); };
 
     // non-empty rows -> compact numbering
     DevBuf<u32> cid(rows + 1);
@@ -377,39 +623,52 @@ void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
         st.launches++;
         cstart = cstart_buf.get();
     }
-
     K.data.alloc(((size_t)num_chunks + 1) * (kChunkBytes / 16));
     k_chunk_scatter<<<grid_for(padded, 256 * 4), 256, 0, s>>>(X.idx, X.val, nnz, padded, K.data);
     LAS2_LAUNCH_CHECK();
     st.launches++;
-    K.chunk_row.alloc((size_t)num_chunks + 1);
-    k_chunk_rows<<<cdiv((u64)num_chunks + 1, 256), 256, 0, s>>>(cstart, nc, num_chunks, K.chunk_row);
-    LAS2_LAUNCH_CHECK();
-    st.launches++;
-    K.fix_row.alloc(num_chunks);
-    K.fix_first.alloc(num_chunks);
-    k_chunk_fix_list<<<cdiv(num_chunks, 256), 256, 0, s>>>(cstart, K.has_empty_rows ? K.rowmap.get() : nullptr, K.chunk_row,
-                                                          num_chunks, K.fix_row, K.fix_first);
-    LAS2_LAUNCH_CHECK();
-    st.launches++;
-    k_chunk_flags<<<grid_for((u64)nc + 1, 256), 256, 0, s>>>(cstart, nc, K.data, K.chunk_row);
-    LAS2_LAUNCH_CHECK();
-    st.launches++;
-    K.carry.alloc(num_chunks);
-    K.head.alloc(num_chunks);
-    LAS2_CUDA(cudaMemsetAsync(K.carry.get(), 0, num_chunks * sizeof(double), s));
-    LAS2_CUDA(cudaMemsetAsync(K.head.get(), 0, num_chunks * sizeof(double), s));
+    finalize_chunks(K, cstart, K.has_empty_rows ? K.rowmap.get() : nullptr, nc, num_chunks, s, st);
     LAS2_CUDA(cudaStreamSynchronize(s)); // cid / cstart_buf go out of scope
+    K.stream_bytes = (u64)num_chunks * kChunkBytes + 4 * (u64)num_chunks + 8 * X.cols + 8 * X.rows;
+}
 
-    K.rows = X.rows; K.cols = X.cols; K.num_chunks = num_chunks;
+} // namespace
+
+// Builds X.chk from the natural CSR arrays of X (device-side, deterministic).
+void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
+    ChunkStream &K = X.chk;
+    K = ChunkStream();
+    // SVDLAS2_SPMV: unset = this format for matrices large enough to fill the persistent kernel; "chunk" = always;
+    // anything else (e.g. "tile", "blocked") = never (the older kernels stay reachable for comparison).
+    // SVDLAS2_SLABS: unset = slab mode where a (slab, row) piece holds >= 4 entries on average; 0 = never; 1 = always.
+    const char *want = std::getenv("SVDLAS2_SPMV");
+    const bool force = want && std::string(want) == "chunk";
+    if (want && want[0] && !force) return;
+    if (X.nnz == 0 || X.rows == 0) return;
+    if (!force && X.nnz < (u64)8 * kNumSMs * kSpmvTile) return;
+    if (X.cols >= kChunkFlag || X.rows >= kChunkFlag || X.nnz + 2 * (u64)kChunkNnz >= ((u64)1 << 32)) return;
+    const char *sl = std::getenv("SVDLAS2_SLABS");
+    const char slab_mode = (sl && sl[0]) ? sl[0] : 'a';
+    bool done = false;
+    // Slabs only when the hot prefix cannot do the job (cfg 2: B, 65 % of whose gathers hit the first 8192 entries of
+    // x, runs 0.12 ms with the prefix and 0.19 ms in slab mode; B', whose gathered vector t has no popular prefix,
+    // 0.19 ms without slabs and 0.15 ms with them).
+    if (slab_mode == '1' || (slab_mode != '0' && X.hot_entries == 0)) done = build_slab_stream(X, K, slab_mode == '1', s, st);
+    if (!done) { K = ChunkStream(); build_plain_stream(X, K, s, st); }
+    K.rows = X.rows; K.cols = X.cols;
     K.active = true;
 }
 
 void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
     const ChunkStream &K = A.chk;
-    u32 hot = g_spmv_hot_entries >= 0 ? (u32)g_spmv_hot_entries : std::min<u32>(A.hot_entries, kChunkHotDefault);
-    hot = std::min<u32>(hot, kChunkHotMax);
-    hot = (u32)std::min<u64>(hot, K.cols);
+    u32 hot = 0;
+    if (K.slabs) {
+        hot = kSlabWidth;
+    } else {
+        hot = g_spmv_hot_entries >= 0 ? (u32)g_spmv_hot_entries : std::min<u32>(A.hot_entries, kChunkHotDefault);
+        hot = std::min<u32>(hot, kChunkHotMax);
+        hot = (u32)std::min<u64>(hot, K.cols);
+    }
     const size_t smem = std::min<size_t>(chunk_smem_bytes(hot) + (size_t)g_chunk_smem_pad_kb * 1024, 227 * 1024);
     // The shared-memory carve-out is set explicitly to what this launch needs: left to itself the driver picks the
     // carve-out that would fit the most CTAs per SM (e.g. 196 KB for a 98 KB kernel), and the gathers then lose the
@@ -422,19 +681,34 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
         LAS2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         cached = carve;
     };
-    if (K.has_empty_rows) LAS2_CUDA(cudaMemsetAsync(y, 0, K.rows * sizeof(double), s));
-    const u32 grid = std::min<u32>(kNumSMs, cdiv(K.num_chunks, kChunkWarps));
-    const u32 *rowmap = K.has_empty_rows ? K.rowmap.get() : nullptr;
-    if (hot > 0) {
-        configure((const void *)k_spmv_chunk<true>, g_chunk_carve_hot);
-        k_spmv_chunk<true><<<grid, kChunkThreads, smem, s>>>(K.data, K.chunk_row, rowmap, x, y, K.carry, K.head, K.num_chunks, hot);
-    } else {
-        configure((const void *)k_spmv_chunk<false>, g_chunk_carve_cold);
-        k_spmv_chunk<false><<<grid, kChunkThreads, smem, s>>>(K.data, K.chunk_row, rowmap, x, y, K.carry, K.head, K.num_chunks, 0u);
-    }
-    k_chunk_fixup<<<cdiv(K.num_chunks, 256), 256, 0, s>>>(K.fix_row, K.fix_first, K.carry, K.head, y, K.num_chunks);
-    LAS2_LAUNCH_CHECK();
+    // launch shape: 32 warps x 1 stage unless the knob "spmv_shape" says 16 x 2 (value 16)
+    const bool wide = g_chunk_shape != 16;
+    const u32 warps = wide ? 32 : 16;
+    const u32 grid = std::min<u32>(kNumSMs, cdiv(K.num_chunks, warps));
+    const u32 *rowmap = (!K.slabs && K.has_empty_rows) ? K.rowmap.get() : nullptr;
+    double *out = K.slabs ? K.part.get() : y;
+    const int mode = K.slabs ? 2 : (hot > 0 ? 1 : 0);
+    if (mode != 2 && K.has_empty_rows) LAS2_CUDA(cudaMemsetAsync(y, 0, K.rows * sizeof(double), s));
+#define LAS2_CHUNK_LAUNCH(MODE, WARPS, STAGES, SLOT)                                                                   \
+    do {                                                                                                               \
+        configure((const void *)k_spmv_chunk<MODE, WARPS, STAGES>, g_chunk_carve[SLOT]);                               \
+        launch_pdl(k_spmv_chunk<MODE, WARPS, STAGES>, dim3(grid), dim3(WARPS * 32), smem, s, (const uint4 *)K.data,       \
+                   (const u32 *)K.chunk_row, rowmap, x, out, (double *)K.carry, (double *)K.head, K.num_chunks,          \
+                   mode == 2 ? 0u : hot, (const u32 *)K.slab_chunk_start, K.nslabs, (u32)K.cols);                      \
+    } while (0)
+    if (mode == 2) { if (wide) LAS2_CHUNK_LAUNCH(2, 32, 1, 0); else LAS2_CHUNK_LAUNCH(2, 16, 2, 1); }
+    else if (mode == 1) { if (wide) LAS2_CHUNK_LAUNCH(1, 32, 1, 2); else LAS2_CHUNK_LAUNCH(1, 16, 2, 3); }
+    else { if (wide) LAS2_CHUNK_LAUNCH(0, 32, 1, 4); else LAS2_CHUNK_LAUNCH(0, 16, 2, 5); }
+#undef LAS2_CHUNK_LAUNCH
+    launch_pdl(k_chunk_fixup, dim3(cdiv(K.num_chunks, 256)), dim3(256), 0, s, (const u32 *)K.fix_row, (const u32 *)K.fix_first,
+               (const double *)K.carry, (const double *)K.head, out, K.num_chunks);
     if (launches) *launches += 2;
+    if (mode == 2) {
+        launch_pdl(k_slab_reduce, dim3(cdiv(K.rows * kReduceLanes, 256)), dim3(256), 0, s, (const u32 *)K.piece_id,
+                   (const double *)K.part, (u64)K.rows, K.nslabs, y);
+        if (launches) *launches += 1;
+    }
+    LAS2_LAUNCH_CHECK();
 }
 
 } // namespace las2

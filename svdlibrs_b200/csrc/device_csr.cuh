@@ -55,19 +55,33 @@ constexpr u32 kChunkNnz = 32 * kChunkE;       // 256
 constexpr u32 kChunkBytes = kChunkNnz * 12;   // 3072
 constexpr u32 kChunkFlag = 0x80000000u;
 
+// Slab mode (matrices with enough entries per (column block, row) piece): the same chunk stream, but ordered
+// (slab, row, column) with slab = column / kSlabWidth and LOCAL column indices, so that while a CTA works inside a slab
+// every gather is a shared-memory read of the slab's 128 KB slice of x.  A "row" of the stream is then a non-empty
+// (slab, row) piece; the kernel writes one partial sum per piece (indexed by the piece's running number) and
+// k_slab_reduce adds the pieces of each row in slab order.
+constexpr u32 kSlabWidth = 16384;
+
 struct ChunkStream {
     bool active = false;
+    bool slabs = false;
     u64 rows = 0, cols = 0;
     u32 num_chunks = 0;
-    u32 nonempty_rows = 0;
+    u32 nonempty_rows = 0;   // plain: rows with entries; slab mode: non-empty (slab, row) pieces
     bool has_empty_rows = false;
+    u32 nslabs = 0;
     DevBuf<uint4> data;      // (num_chunks + 1) * 192
     DevBuf<u32> chunk_row;   // num_chunks + 1: index (among the non-empty rows) of the first row that STARTS at or after
                              // the chunk's first element; bit 31: some lane of the chunk holds two or more row starts
-    DevBuf<u32> rowmap;      // non-empty row index -> row (empty when every row is non-empty)
+    DevBuf<u32> rowmap;      // non-empty row index -> row (plain mode only, empty when every row is non-empty)
     DevBuf<double> carry;    // num_chunks: sum of the piece that is still open at the chunk's end
     DevBuf<double> head;     // num_chunks: sum of the piece that was open at the chunk's start, up to the first row start
     DevBuf<u32> fix_row, fix_first; // num_chunks: row completed by chunk b's head (or ~0u) and the chunk it started in
+    // slab mode
+    DevBuf<u32> slab_chunk_start;   // nslabs + 1
+    DevBuf<u32> piece_id;           // nslabs * rows + 1: running number of piece (slab, row) (exclusive scan of "non-empty")
+    DevBuf<double> part;            // one partial sum per piece
+    u64 stream_bytes = 0;           // bytes one SpMV moves with this format (reporting)
 };
 
 struct DeviceCsr {

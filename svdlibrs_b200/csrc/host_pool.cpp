@@ -12,8 +12,10 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -57,10 +59,34 @@ Pool &pool() {
     return *p;
 }
 
-void first_touch(char *p, size_t n) {
-    unsigned nt = std::thread::hardware_concurrency();
-    nt = std::max(1u, std::min(16u, nt));
-    if (n < (size_t)64 << 20) nt = 1;
+// CPUs this process may actually burn: the cgroup quota when there is one (a burst of 16 touch threads inside a
+// container with a smaller CFS quota gets the whole process throttled for the rest of the period -- seen on the
+// B200 box as 0.2-0.8 s stalls of the launching thread right after an allocation), else the visible cores.
+unsigned usable_cpus() {
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    double quota = 0.0;
+    if (FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) { // cgroup v2: "<quota|max> <period>"
+        char q[64]; long period = 0;
+        if (std::fscanf(f, "%63s %ld", q, &period) == 2 && period > 0 && std::strcmp(q, "max") != 0) quota = std::atof(q) / (double)period;
+        std::fclose(f);
+    } else if (FILE *g = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { // cgroup v1
+        long q = -1, period = 100000;
+        if (std::fscanf(g, "%ld", &q) != 1) q = -1;
+        std::fclose(g);
+        if (FILE *h = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (std::fscanf(h, "%ld", &period) != 1) period = 100000; std::fclose(h); }
+        if (q > 0 && period > 0) quota = (double)q / (double)period;
+    }
+    if (quota >= 1.0) hw = std::min<unsigned>(hw, (unsigned)quota);
+    return hw;
+}
+
+void first_touch(char *p, size_t n, bool single) {
+    static const unsigned want = [] {
+        if (const char *e = std::getenv("SVDLAS2_TOUCH_THREADS")) return (unsigned)std::max(1, std::atoi(e));
+        return std::max(1u, std::min(8u, usable_cpus() / 2)); // leave cores to the launching thread and the driver
+    }();
+    unsigned nt = want;
+    if (n < (size_t)256 << 20 || single) nt = 1;
     auto work = [p, n, nt](unsigned t) {
         size_t a = n / nt * t, b = (t == nt - 1) ? n : n / nt * (t + 1);
         a = a / 4096 * 4096;
@@ -98,13 +124,15 @@ void *host_acquire(size_t bytes) {
         }
     }
     const size_t cap = (bytes + kHuge - 1) / kHuge * kHuge;
+    // debugging switches (SVDLAS2_HOST_POOL): "nothp" = no huge-page advice, "touch1" = single-threaded first touch
+    static const std::string mode = [] { const char *e = std::getenv("SVDLAS2_HOST_POOL"); return std::string(e ? e : ""); }();
     void *p = mmap(nullptr, cap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (p == MAP_FAILED)
         throw Error(SVDLAS2_ERR_ALLOC, "host result allocation of " + std::to_string(bytes) + " bytes failed");
-    madvise(p, cap, MADV_HUGEPAGE); // advisory: without THP the block is still correct, only slower to pin
+    if (mode != "nothp") madvise(p, cap, MADV_HUGEPAGE); // advisory: without THP the block is still correct, only slower to pin
     const bool trace = std::getenv("SVDLAS2_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    first_touch((char *)p, cap);
+    first_touch((char *)p, cap, mode == "touch1");
     const auto t1 = std::chrono::steady_clock::now();
     Kind kind = Kind::Registered;
     if (cudaHostRegister(p, cap, cudaHostRegisterPortable) != cudaSuccess) {

@@ -85,7 +85,7 @@ struct Solver {
         w5.assign(iters + 2, 0.0);
         LAS2_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         const u64 want = dims * (M + N) * sizeof(double);
-        if (want <= host_prefetch_limit()) { // only when the upper bound d <= dims is affordable
+        if (want <= host_prefetch_limit() && !std::getenv("SVDLAS2_NO_PREFETCH")) { // only when the upper bound d <= dims is affordable
             const int dev = op.device;
             const size_t bm = std::max<u64>(1, dims * M) * sizeof(double), bn = std::max<u64>(1, dims * N) * sizeof(double);
             fut_m = std::async(std::launch::async, [dev, bm] { cudaSetDevice(dev); return host_acquire(bm); });
@@ -462,10 +462,13 @@ struct Solver {
         DevBuf<double> U((size_t)d * mcols);
         DevBuf<double> S(d);
         DevBuf<double> nrm2(d); // |B_g v_i|^2 per triplet (summed over ranks when sharded)
+        double tmax[4] = {0, 0, 0, 0}; // trace: slowest host-side call of each kind in the loop below
         for (u64 i = 0; i < d; i++) {
             double *vi = V.get() + i * ld;
             double *ui = U.get() + i * mcols;
+            const double tl0 = trace ? wall() : 0.0;
             spmv(op.B, vi, ui, s, &prof.n_kernel_launches);
+            const double tl1 = trace ? wall() : 0.0;
             prof.n_spmv += 1;
             vec_sumsq_any(ui, mcols, slot[0], s);
             PartialSlot t2 = slot[0];
@@ -480,10 +483,19 @@ struct Solver {
             }
             vec_sigma_scale(ui, mcols, t2, S.get() + i, s);
             prof.n_kernel_launches += 1;
+            const double tl2 = trace ? wall() : 0.0;
             LAS2_CUDA(cudaEventRecord(ev, s));
             LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+            const double tl3 = trace ? wall() : 0.0;
             LAS2_CUDA(cudaMemcpyAsync(hU + i * mcols, ui, mcols * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
+            if (trace) {
+                const double tl4 = wall();
+                tmax[0] = std::max(tmax[0], tl1 - tl0); tmax[1] = std::max(tmax[1], tl2 - tl1);
+                tmax[2] = std::max(tmax[2], tl3 - tl2); tmax[3] = std::max(tmax[3], tl4 - tl3);
+            }
         }
+        if (trace) fprintf(stderr, "[svdlas2] ritvec: slowest host call in the tail loop: spmv %.4f s, sumsq/scale %.4f s, event %.4f s, memcpyAsync %.4f s\n",
+                           tmax[0], tmax[1], tmax[2], tmax[3]);
         LAS2_CUDA(cudaMemcpyAsync(hS, S.get(), d * sizeof(double), cudaMemcpyDeviceToHost, s));
         LAS2_CUDA(cudaStreamSynchronize(s));
         if (trace) fprintf(stderr, "[svdlas2] ritvec: sigma/U tail (%llu SpMV) in %.3f s\n", (unsigned long long)d, wall() - tt0);

@@ -37,6 +37,15 @@ struct Error : std::runtime_error {
 
 #define LAS2_LAUNCH_CHECK() LAS2_CUDA(cudaGetLastError())
 
+// Device memory comes from the device's stream-ordered pool with the release threshold lifted, so that the buffers a
+// solve frees (Lanczos panel, U/V, upload scratch) are handed back to the next allocation in microseconds instead
+// of being unmapped and mapped again by cudaFree / cudaMalloc (tens of milliseconds of jitter per solve on B200).
+// device_alloc returns memory that is immediately usable on any stream; device_free waits for the device like
+// cudaFree does.  (util.cu)
+void *device_alloc(size_t bytes);
+void device_free(void *p);
+void device_pool_trim(); // give cached device memory back to the driver
+
 template <typename T>
 class DevBuf {
   public:
@@ -54,16 +63,10 @@ class DevBuf {
         release();
         n_ = n;
         if (n == 0) return;
-        cudaError_t e = cudaMalloc(&p_, n * sizeof(T));
-        if (e != cudaSuccess) {
-            p_ = nullptr; n_ = 0;
-            cudaGetLastError();
-            throw Error(SVDLAS2_ERR_ALLOC, "cudaMalloc of " + std::to_string(n * sizeof(T)) + " bytes failed: " +
-                                               cudaGetErrorString(e));
-        }
+        p_ = static_cast<T *>(device_alloc(n * sizeof(T)));
     }
     void release() {
-        if (p_) cudaFree(p_);
+        if (p_) device_free(p_);
         p_ = nullptr; n_ = 0;
     }
     T *get() const { return p_; }

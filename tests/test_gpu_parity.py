@@ -132,14 +132,15 @@ def test_coo_duplicates_are_summed(las2, oracle):
     assert_svd_parity(got, ref)
 
 
-@pytest.mark.parametrize("spmv", ["", "chunk"])
+@pytest.mark.parametrize("spmv", ["", "chunk", "chunk+slabs"])
 def test_spmv_ragged_rows(las2, oracle, spmv, monkeypatch):
     """rows of length 0, 1 and > one nnz-tile, leading / trailing empty rows, tile-straddling rows; with the
     small-matrix kernel (default at this size) and with the warp-chunk stream forced (rows shorter than a lane's 8
     elements, rows spanning > 32 chunks, empty rows -> row map)"""
-    monkeypatch.setenv("SVDLAS2_SPMV", spmv)
+    monkeypatch.setenv("SVDLAS2_SPMV", spmv.split("+")[0])
+    monkeypatch.setenv("SVDLAS2_SLABS", "1" if "slabs" in spmv else "0")
     rng = np.random.default_rng(11)
-    nrows, ncols = 700, 9000
+    nrows, ncols = 700, (40000 if "slabs" in spmv else 9000)  # 40000 columns: three 16384-column slabs
     lens = np.zeros(nrows, dtype=int)
     lens[5] = 9000; lens[6] = 1; lens[7] = 5000; lens[300:310] = 33; lens[310:340] = 32; lens[400] = 4097
     lens[500:650] = rng.integers(0, 60, 150)
@@ -221,7 +222,7 @@ def test_iterations_and_kappa_parameters(las2, oracle):
 
 
 @pytest.mark.parametrize("variant,hot", [(0, -1), (1, -1), (2, -1), (3, 0), (3, 5), (3, 1000), (3, -1), (4, -1), (5, -1), (5, 0), (5, 7),
-                                         (6, -1), (6, 0), (6, 7), (6, 4096), (6, 8192)])
+                                         (6, -1), (6, 0), (6, 7), (6, 4096), (6, 8192), (7, -1)])
 def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
     """all SpMV kernels (warp-chunk stream with several shared-memory prefix sizes, one-CTA-per-tile with 256/128/512
     threads, persistent hot-prefix kernel, blocked/interleaved tile streams) on ragged + power-law inputs, both
@@ -230,9 +231,12 @@ def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
     from svdlibrs_b200 import synthetic
     # test variant -> (library variant, formats built at upload): 4 = slabs where they pay, 5 = tile stream without
     # slabs, 6 = the warp-chunk stream (the default of large matrices, forced here at test size)
-    os.environ["SVDLAS2_SPMV"] = "chunk" if variant == 6 else "tile"
+    # (forced at test size); 7 = the same stream in slab mode (column blocks of 16384 gathered from shared memory)
+    os.environ["SVDLAS2_SPMV"] = "chunk" if variant >= 6 else "tile"
+    os.environ["SVDLAS2_SLABS"] = "1" if variant == 7 else "0"
     os.environ["SVDLAS2_BLOCKED"] = {4: "1", 5: "2"}.get(variant, "0")
-    variant = {5: 4, 6: 5}.get(variant, variant)
+    slabs = variant == 7
+    variant = {5: 4, 6: 5, 7: 5}.get(variant, variant)
     rng = np.random.default_rng(21)
     mats = [synthetic.make("cfg2", scale=0.01)[0],
             sp.random(3000, 5000, density=0.004, format="csr", random_state=rng)]
@@ -240,6 +244,9 @@ def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
     rows = np.concatenate([np.full(l, i) for i, l in enumerate(lens)])
     cols = np.concatenate([np.sort(rng.choice(7000, size=l, replace=False)) for l in lens])
     mats.append(sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(400, 7000)))
+    if slabs:  # wide enough for several slabs in both orientations; short pieces (slow path) and empty pieces
+        mats.append(sp.random(30000, 50000, density=0.0004, format="csr", random_state=rng))
+        mats.append(synthetic.make("cfg3", scale=0.02)[0])
     for A in mats:
         with las2.Operator(A) as op:
             op.set("spmv_variant", variant)
@@ -254,6 +261,7 @@ def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
                 op.set("spmv_hot", -1)
                 os.environ.pop("SVDLAS2_BLOCKED", None)
                 os.environ.pop("SVDLAS2_SPMV", None)
+                os.environ.pop("SVDLAS2_SLABS", None)
 
 
 def test_cfg2_full_size_invariants(las2):
