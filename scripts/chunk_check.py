@@ -37,7 +37,7 @@ with las2.Operator(A) as op:
             op.set("spmv_variant", v); op.set("spmv_hot", -1)
             t = op.time_opb(reps=a.reps, flush_l2=False)
             print(json.dumps(dict(variant=v, ms_opb=round(t["ms_per_opb"], 4), ms_b=round(t["ms_spmv_b"], 4), ms_bt=round(t["ms_spmv_bt"], 4))), flush=True)
-    op.set("spmv_variant", -1); op.set("spmv_hot", -1); op.set("spmv_smem_pad_kb", 0); op.set("spmv_carveout", -1); op.set("spmv_shape", 32); op.set("spmv_pdl", 1)
+    op.set("spmv_variant", -1); op.set("spmv_hot", -1); op.set("spmv_smem_pad_kb", 0); op.set("spmv_carveout", -1); op.set("spmv_shape", 32); op.set("spmv_pdl", -1)
     import time
     for i in range(2):
         t0 = time.perf_counter(); r = op.solve(dims, random_seed=12345); dt = time.perf_counter() - t0

@@ -16,8 +16,11 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--variant", type=int, default=-1)
 ap.add_argument("--flush", type=int, default=0)
 ap.add_argument("--hot", type=int, default=-1)
+ap.add_argument("--shard", type=int, default=1, help="profile the first of this many row shards (multi-GPU shard shape)")
 a = ap.parse_args()
 A, dims = synthetic.make(a.workload, scale=a.scale)
+if a.shard > 1:
+    A = A[: A.shape[0] // a.shard].tocsr()
 with las2.Operator(A) as op:
     op.set("spmv_variant", a.variant)
     op.set("spmv_hot", a.hot)

@@ -187,50 +187,60 @@ __global__ void k_slab_scatter(const u32 *__restrict__ off, const u32 *__restric
     }
 }
 
-// y[r] = sum of the partials of the pieces (slab, r).  Eight lanes share a row: lane q sums slabs q, q+8, q+16, ... in
-// ascending order (piece numbers first -- static, fetched before the grid dependency resolves -- then the partials,
-// independent loads), and a fixed three-step shuffle tree adds the eight sums.  Consecutive groups take consecutive
-// rows, so for a fixed slab the piece numbers and partials of a warp's four rows are adjacent in memory.
-constexpr int kReduceLanes = 8;
-constexpr int kReduceMaxPerLane = 16; // slabs per lane held in registers; more slabs fall back to the loop below
-__global__ void __launch_bounds__(256)
-k_slab_reduce(const u32 *__restrict__ piece_id, const double *__restrict__ part, u64 rows, u32 nslabs,
-              double *__restrict__ y) {
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 r = gid / kReduceLanes;
-    const u32 q = (u32)(gid % kReduceLanes);
+// slot[v] = running number of piece v when it has entries, kNoPiece otherwise (one load per (slab, row) in the reduce)
+constexpr u32 kNoPiece = 0xffffffffu;
+__global__ void k_piece_slots(const u32 *__restrict__ piece_id, u64 npieces, u32 *__restrict__ slot) {
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; v < npieces; v += stride) {
+        const u32 id = piece_id[v];
+        slot[v] = piece_id[v + 1] > id ? id : kNoPiece;
+    }
+}
+
+// y[r] = sum of the partials of the pieces (slab, r).  A CTA of 8 warps owns 32 consecutive rows; warp w sums slabs
+// w, w+8, w+16, ... in ascending order with lane = row, so the slot loads of a warp are one 128-byte line and the
+// partials it then fetches are (nearly) consecutive doubles; the eight per-warp sums of a row are added in warp order
+// through shared memory.  Every order is fixed.  The slot numbers are static: with programmatic dependent launch
+// they are fetched while the kernels before this one drain.
+constexpr int kReduceWarps = 8;
+constexpr int kReduceMaxPerWarp = 16; // slabs per warp held in registers; more slabs fall back to a loop
+__global__ void __launch_bounds__(kReduceWarps * 32)
+k_slab_reduce(const u32 *__restrict__ slot, const double *__restrict__ part, u64 rows, u32 nslabs, double *__restrict__ y) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    __shared__ double sums[kReduceWarps][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u64 r = (u64)blockIdx.x * 32 + lane;
     const bool live = r < rows;
     double s = 0.0;
-    if (nslabs <= kReduceLanes * kReduceMaxPerLane) {
-        u32 id[kReduceMaxPerLane];
-        bool on[kReduceMaxPerLane];
+    if (nslabs <= kReduceWarps * kReduceMaxPerWarp) {
+        u32 id[kReduceMaxPerWarp];
 #pragma unroll
-        for (int j = 0; j < kReduceMaxPerLane; j++) {
-            const u32 b = q + j * kReduceLanes;
-            on[j] = false;
-            if (live && b < nslabs) {
-                const u64 v = (u64)b * rows + r;
-                id[j] = piece_id[v];
-                on[j] = piece_id[v + 1] > id[j];
-            }
+        for (int j = 0; j < kReduceMaxPerWarp; j++) {
+            const u32 b = w + j * kReduceWarps;
+            id[j] = (live && b < nslabs) ? slot[(u64)b * rows + r] : kNoPiece;
         }
         cudaGridDependencySynchronize();
-        double p[kReduceMaxPerLane];
+        double p[kReduceMaxPerWarp];
 #pragma unroll
-        for (int j = 0; j < kReduceMaxPerLane; j++) p[j] = on[j] ? part[id[j]] : 0.0;
+        for (int j = 0; j < kReduceMaxPerWarp; j++) p[j] = id[j] != kNoPiece ? part[id[j]] : 0.0;
 #pragma unroll
-        for (int j = 0; j < kReduceMaxPerLane; j++) s += p[j];
+        for (int j = 0; j < kReduceMaxPerWarp; j++) s += p[j];
     } else {
         cudaGridDependencySynchronize();
-        for (u32 b = q; live && b < nslabs; b += kReduceLanes) {
-            const u64 v = (u64)b * rows + r;
-            const u32 id = piece_id[v];
-            if (piece_id[v + 1] > id) s += part[id];
+        for (u32 b = w; live && b < nslabs; b += kReduceWarps) {
+            const u32 id = slot[(u64)b * rows + r];
+            if (id != kNoPiece) s += part[id];
         }
     }
+    sums[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && live) {
+        double t = sums[0][lane];
 #pragma unroll
-    for (int o = 1; o < kReduceLanes; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (live && q == 0) y[r] = s;
+        for (int k = 1; k < kReduceWarps; k++) t += sums[k][lane];
+        y[r] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -252,7 +262,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity) {
 }
 __device__ __forceinline__ double u2d(u32 lo, u32 hi) { return __hiloint2double((int)hi, (int)lo); }
 
-constexpr size_t kChunkBarBytes = 256; // up to 32 mbarriers
+constexpr size_t kChunkBarBytes = 384; // up to 32 stage mbarriers + the slice mbarrier of the slab mode
 size_t chunk_smem_bytes(u32 hot) { return kChunkBarBytes + (size_t)kChunkStageBytesTotal + (size_t)hot * sizeof(double); }
 
 // One warp's walk over the chunks first, first + step, ... < stop.  MODE 0: every gather through L1; 1: columns below
@@ -411,6 +421,15 @@ k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, 
     }
     __syncwarp();
     u32 phases = 0;
+    unsigned long long *slice_bar = bars + WARPS * STAGES;
+    u32 slice_phase = 0;
+    if (MODE == 2) {
+        if (threadIdx.x == 0) {
+            mbar_init(slice_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
 
     // Programmatic dependent launch: up to here only this kernel's own shared memory was touched; x (written by the
     // kernel before this one) is read and y / carry / head are written only after the preceding grid has completed.
@@ -426,8 +445,17 @@ k_spmv_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, 
             const u32 stop = min(hi, slab_chunk_start[sl + 1]);
             __syncthreads(); // every warp is done with the previous slice
             const u32 col0 = sl * kSlabWidth;
-            for (u32 i = threadIdx.x; i < kSlabWidth; i += kChunkThreads)
-                xs[i] = (col0 + i < cols) ? ld_gather_f64(x + col0 + i, pol_keep) : 0.0;
+            const u32 n = min(kSlabWidth, cols - col0);
+            if (threadIdx.x == 0) {
+                // one bulk copy for the slice (an even number of doubles: 16-byte granularity), the odd one by hand
+                const u32 bytes = (n & ~1u) * (u32)sizeof(double);
+                if (bytes) {
+                    mbar_expect_tx(slice_bar, bytes);
+                    bulk_load(xs, x + col0, bytes, slice_bar, pol_keep);
+                }
+                if (n & 1u) xs[n - 1] = ld_gather_f64(x + col0 + n - 1, pol_keep);
+            }
+            if (n > 1) { mbar_wait(slice_bar, slice_phase); slice_phase ^= 1u; }
             __syncthreads();
             chunk_walk<2, STAGES>(cur + warp, stop, kChunkWarps, lane, bar, stage, phases, xs, 0u, data, chunk_row, rowmap, x, y,
                           carry, head, pol_stream, pol_keep);
@@ -482,7 +510,7 @@ int g_chunk_carve[6] = {-2, -2, -2, -2, -2, -2}; // carve-out currently set on e
 } // namespace
 
 int g_chunk_smem_pad_kb = 0;  // tuning knob "spmv_smem_pad_kb": extra (unused) dynamic shared memory
-int g_chunk_pdl = 1;           // tuning knob "spmv_pdl": programmatic dependent launch of the SpMV kernel chain
+int g_chunk_pdl = -1;          // tuning knob "spmv_pdl": programmatic dependent launch of the SpMV kernel chain (-1: SVDLAS2_PDL, default on)
 int g_chunk_shape = 32;        // tuning knob "spmv_shape": 32 = 32 warps x 1 stage, 16 = 16 warps x 2 stages
 int g_chunk_carveout_pct = -1; // tuning knob "spmv_carveout": shared-memory carve-out in percent of 228 KB (-1: exact fit)
 
@@ -490,15 +518,26 @@ int g_chunk_carveout_pct = -1; // tuning knob "spmv_carveout": shared-memory car
 
 namespace {
 
+// Programmatic dependent launch of the SpMV kernel chain (~2 % per opb at cfg 2; Nsight Compute lists and times the
+// kernels either way).  Knob "spmv_pdl" or SVDLAS2_PDL=0 turns it off.
+bool chunk_pdl_enabled() {
+    static const int env = [] { const char *e = std::getenv("SVDLAS2_PDL"); return e ? std::atoi(e) : -1; }();
+    return g_chunk_pdl >= 0 ? g_chunk_pdl != 0 : env != 0;
+}
+
 // Launch with programmatic stream serialisation: the kernel may start while its predecessor in the stream drains; it
 // must call cudaGridDependencySynchronize() before touching anything the predecessor wrote (or still reads).
 template <typename... KArgs, typename... Args>
 void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    if (!chunk_pdl_enabled()) { // the plain launch path: visible to every profiler
+        kernel<<<grid, block, smem, s>>>(static_cast<KArgs>(args)...);
+        return;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_chunk_pdl ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     LAS2_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
@@ -587,6 +626,14 @@ bool build_slab_stream(DeviceCsr &X, ChunkStream &K, bool force, cudaStream_t s,
     LAS2_LAUNCH_CHECK();
     st.launches += 2;
     finalize_chunks(K, cstart, nullptr, nc, num_chunks, s, st);
+    {
+        DevBuf<u32> slots(npieces);
+        k_piece_slots<<<grid_for(npieces, 256 * 4), 256, 0, s>>>(K.piece_id, npieces, slots);
+        LAS2_LAUNCH_CHECK();
+        st.launches++;
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        K.piece_id = std::move(slots); // from here on: slot numbers (kNoPiece for empty pieces)
+    }
     K.part.alloc(nc);
     LAS2_CUDA(cudaMemsetAsync(K.part.get(), 0, (size_t)nc * sizeof(double), s));
     LAS2_CUDA(cudaStreamSynchronize(s)); // scratch and host vectors go out of scope
@@ -653,7 +700,10 @@ void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
     // Slabs only when the hot prefix cannot do the job (cfg 2: B, 65 % of whose gathers hit the first 8192 entries of
     // x, runs 0.12 ms with the prefix and 0.19 ms in slab mode; B', whose gathered vector t has no popular prefix,
     // 0.19 ms without slabs and 0.15 ms with them).
-    if (slab_mode == '1' || (slab_mode != '0' && X.hot_entries == 0)) done = build_slab_stream(X, K, slab_mode == '1', s, st);
+    // And only for matrices (shards) big enough to amortise the per-launch cost of the mode (slice loads, the reduce
+    // kernel: ~20 us against ~1.3 ps saved per non-zero).
+    if (slab_mode == '1' || (slab_mode != '0' && X.hot_entries == 0 && X.nnz >= (u64)20000000))
+        done = build_slab_stream(X, K, slab_mode == '1', s, st);
     if (!done) { K = ChunkStream(); build_plain_stream(X, K, s, st); }
     K.rows = X.rows; K.cols = X.cols;
     K.active = true;
@@ -704,7 +754,7 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
                (const double *)K.carry, (const double *)K.head, out, K.num_chunks);
     if (launches) *launches += 2;
     if (mode == 2) {
-        launch_pdl(k_slab_reduce, dim3(cdiv(K.rows * kReduceLanes, 256)), dim3(256), 0, s, (const u32 *)K.piece_id,
+        launch_pdl(k_slab_reduce, dim3(cdiv(K.rows, 32)), dim3(kReduceWarps * 32), 0, s, (const u32 *)K.piece_id,
                    (const double *)K.part, (u64)K.rows, K.nslabs, y);
         if (launches) *launches += 1;
     }

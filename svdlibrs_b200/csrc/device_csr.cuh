@@ -79,7 +79,7 @@ struct ChunkStream {
     DevBuf<u32> fix_row, fix_first; // num_chunks: row completed by chunk b's head (or ~0u) and the chunk it started in
     // slab mode
     DevBuf<u32> slab_chunk_start;   // nslabs + 1
-    DevBuf<u32> piece_id;           // nslabs * rows + 1: running number of piece (slab, row) (exclusive scan of "non-empty")
+    DevBuf<u32> piece_id;           // nslabs * rows: running number of piece (slab, row), 0xffffffff when it has no entries
     DevBuf<double> part;            // one partial sum per piece
     u64 stream_bytes = 0;           // bytes one SpMV moves with this format (reporting)
 };

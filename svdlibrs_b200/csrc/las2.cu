@@ -462,40 +462,51 @@ struct Solver {
         DevBuf<double> U((size_t)d * mcols);
         DevBuf<double> S(d);
         DevBuf<double> nrm2(d); // |B_g v_i|^2 per triplet (summed over ranks when sharded)
-        double tmax[4] = {0, 0, 0, 0}; // trace: slowest host-side call of each kind in the loop below
-        for (u64 i = 0; i < d; i++) {
-            double *vi = V.get() + i * ld;
-            double *ui = U.get() + i * mcols;
-            const double tl0 = trace ? wall() : 0.0;
-            spmv(op.B, vi, ui, s, &prof.n_kernel_launches);
-            const double tl1 = trace ? wall() : 0.0;
-            prof.n_spmv += 1;
-            vec_sumsq_any(ui, mcols, slot[0], s);
-            PartialSlot t2 = slot[0];
-            prof.n_kernel_launches += 1;
-            if (op.comm) {
-                GatherList g;
-                g.count = 1; g.parts[0] = slot[0].parts; g.nparts[0] = slot[0].nparts;
-                gather_scalars(g, nrm2.get() + i, s);
-                op.comm->allreduce_sum(nrm2.get() + i, 1, s);
-                t2 = PartialSlot{nrm2.get() + i, 1};
-                prof.n_kernel_launches += 1;
+        if (!op.comm) {
+            for (u64 i = 0; i < d; i++) {
+                double *vi = V.get() + i * ld;
+                double *ui = U.get() + i * mcols;
+                spmv(op.B, vi, ui, s, &prof.n_kernel_launches);
+                prof.n_spmv += 1;
+                vec_sumsq_any(ui, mcols, slot[0], s);
+                vec_sigma_scale(ui, mcols, slot[0], S.get() + i, s);
+                prof.n_kernel_launches += 2;
+                LAS2_CUDA(cudaEventRecord(ev, s));
+                LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+                LAS2_CUDA(cudaMemcpyAsync(hU + i * mcols, ui, mcols * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
             }
-            vec_sigma_scale(ui, mcols, t2, S.get() + i, s);
-            prof.n_kernel_launches += 1;
-            const double tl2 = trace ? wall() : 0.0;
-            LAS2_CUDA(cudaEventRecord(ev, s));
-            LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
-            const double tl3 = trace ? wall() : 0.0;
-            LAS2_CUDA(cudaMemcpyAsync(hU + i * mcols, ui, mcols * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
-            if (trace) {
-                const double tl4 = wall();
-                tmax[0] = std::max(tmax[0], tl1 - tl0); tmax[1] = std::max(tmax[1], tl2 - tl1);
-                tmax[2] = std::max(tmax[2], tl3 - tl2); tmax[3] = std::max(tmax[3], tl4 - tl3);
+        } else {
+            // sharded: every rank holds its row slice of B v_i; the squared norms of a batch of triplets are completed
+            // by ONE all-reduce (instead of one latency-bound collective per triplet), then the batch is scaled and
+            // leaves for the host as one contiguous copy
+            constexpr u64 kBatch = 32;
+            for (u64 i0 = 0; i0 < d; i0 += kBatch) {
+                const u64 nb = std::min(kBatch, d - i0);
+                for (u64 i = i0; i < i0 + nb; i++) {
+                    double *ui = U.get() + i * mcols;
+                    spmv(op.B, V.get() + i * ld, ui, s, &prof.n_kernel_launches);
+                    prof.n_spmv += 1;
+                    vec_sumsq_any(ui, mcols, slot[0], s);
+                    GatherList g;
+                    g.count = 1; g.parts[0] = slot[0].parts; g.nparts[0] = slot[0].nparts;
+                    gather_scalars(g, nrm2.get() + i, s);
+                    prof.n_kernel_launches += 2;
+                }
+                op.comm->allreduce_sum(nrm2.get() + i0, nb, s);
+                for (u64 i = i0; i < i0 + nb; i++) {
+                    vec_sigma_scale(U.get() + i * mcols, mcols, PartialSlot{nrm2.get() + i, 1}, S.get() + i, s);
+                    prof.n_kernel_launches += 1;
+                }
+                LAS2_CUDA(cudaEventRecord(ev, s));
+                LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+                LAS2_CUDA(cudaMemcpyAsync(hU + i0 * mcols, U.get() + i0 * mcols, nb * mcols * sizeof(double),
+                                          cudaMemcpyDeviceToHost, copy_stream));
             }
         }
-        if (trace) fprintf(stderr, "[svdlas2] ritvec: slowest host call in the tail loop: spmv %.4f s, sumsq/scale %.4f s, event %.4f s, memcpyAsync %.4f s\n",
-                           tmax[0], tmax[1], tmax[2], tmax[3]);
+        if (trace) {
+            LAS2_CUDA(cudaStreamSynchronize(s));
+            fprintf(stderr, "[svdlas2] ritvec: tail kernels done after %.3f s\n", wall() - tt0);
+        }
         LAS2_CUDA(cudaMemcpyAsync(hS, S.get(), d * sizeof(double), cudaMemcpyDeviceToHost, s));
         LAS2_CUDA(cudaStreamSynchronize(s));
         if (trace) fprintf(stderr, "[svdlas2] ritvec: sigma/U tail (%llu SpMV) in %.3f s\n", (unsigned long long)d, wall() - tt0);
