@@ -27,6 +27,11 @@ SVDLAS2_API int svdlas2_test_refine_bounds(int *enough, double endl, double endr
                                            uint64_t step, double tol, uint64_t *neig);
 /* insert_sort (src/lib.rs:815-825) */
 SVDLAS2_API void svdlas2_test_cosort(uint64_t n, double *keys, double *vals);
+/* GPU tuning hook (needs a device): device-times `reps` reorthogonalisation passes of purge (src/lib.rs:1372-1388) of a
+ * pair (q, r) against `ncols` synthetic Lanczos vectors of length n; outputs milliseconds per pass spent in the
+ * coefficient kernels (c = Q'[q r]) and in the update kernel ([q r] -= Q c).  Returns a status code. */
+SVDLAS2_API int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, int device, double *ms_dots,
+                                        double *ms_update);
 
 #ifdef __cplusplus
 }

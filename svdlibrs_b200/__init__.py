@@ -318,7 +318,7 @@ class Communicator:
         self.rank, self.world_size = rank, world_size
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:  # (_lib is None once the interpreter tears modules down)
             _lib.lib().svdlas2_comm_destroy(self._h)
             self._h = None
 

@@ -6,6 +6,7 @@
 
 #include "host_pool.hpp"
 #include "las2.hpp"
+#include "../../include/svdlas2_testing.h"
 #include "spmv.cuh"
 
 using namespace las2;
@@ -256,6 +257,38 @@ int svdlas2_operator_time_opb(svdlas2_operator *op_, int reps, int flush_l2, dou
         if (ms_spmv_b) *ms_spmv_b = tb / reps;
         if (ms_spmv_bt) *ms_spmv_bt = tbt / reps;
         if (ms_per_opb) *ms_per_opb = (tb + tbt) / reps;
+    });
+}
+
+int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, int device, double *ms_dots, double *ms_update) {
+    if (n == 0 || ncols == 0 || reps < 1) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        if (device >= 0) LAS2_CUDA(cudaSetDevice(device));
+        const u64 ld = (n + 31) / 32 * 32;
+        DevBuf<double> Q((size_t)ld * ncols), a(ld), b(ld), parts(3 * (size_t)kMaxParts);
+        cudaStream_t s;
+        LAS2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        // small entries so that repeated passes stay finite: the values do not matter for the timing
+        LAS2_CUDA(cudaMemsetAsync(Q.get(), 0, (size_t)ld * ncols * sizeof(double), s));
+        LAS2_CUDA(cudaMemsetAsync(a.get(), 0, ld * sizeof(double), s));
+        LAS2_CUDA(cudaMemsetAsync(b.get(), 0, ld * sizeof(double), s));
+        PanelWork pw;
+        PartialSlot sa{parts.get(), 0}, sb{parts.get() + kMaxParts, 0}, sd{parts.get() + 2 * kMaxParts, 0};
+        cudaEvent_t e0, e1, e2;
+        LAS2_CUDA(cudaEventCreate(&e0)); LAS2_CUDA(cudaEventCreate(&e1)); LAS2_CUDA(cudaEventCreate(&e2));
+        double td = 0.0, tu = 0.0;
+        for (int i = -2; i < reps; i++) {
+            panel_cgs2(Q.get(), ld, n, 0, ncols, a.get(), b.get(), pw, &sa, &sb, &sd, s, nullptr, e0, e1, e2);
+            LAS2_CUDA(cudaStreamSynchronize(s));
+            float x = 0.f, y = 0.f;
+            LAS2_CUDA(cudaEventElapsedTime(&x, e0, e1));
+            LAS2_CUDA(cudaEventElapsedTime(&y, e1, e2));
+            if (i >= 0) { td += x; tu += y; }
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        cudaStreamDestroy(s);
+        if (ms_dots) *ms_dots = td / reps;
+        if (ms_update) *ms_update = tu / reps;
     });
 }
 

@@ -23,6 +23,9 @@ struct NcclApi {
     int (*GetUniqueId)(NcclUniqueId *) = nullptr;
     int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool ok = false;
@@ -43,9 +46,13 @@ NcclApi &api() {
         a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
         a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
         a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+        a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(dlsym(h, "ncclBroadcast"));
+        a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
         a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.Broadcast && a.GroupStart && a.GroupEnd && a.CommDestroy &&
+               a.GetErrorString;
         if (!a.ok) a.why = "libnccl.so.2 lacks a required symbol";
     });
     return a;
@@ -90,6 +97,18 @@ Comm::~Comm() {
 void Comm::allreduce_sum(double *buf, uint64_t n, cudaStream_t s) {
     if (world_ == 1) return;
     check(api().AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, nccl_comm_, s), "ncclAllReduce");
+}
+
+void Comm::allgather_ranges(double *buf, const uint64_t *offs, cudaStream_t s) {
+    if (world_ == 1) return;
+    NcclApi &a = api();
+    check(a.GroupStart(), "ncclGroupStart");
+    for (int g = 0; g < world_; g++) {
+        const uint64_t cnt = offs[g + 1] - offs[g];
+        if (cnt == 0) continue;
+        check(a.Broadcast(buf + offs[g], buf + offs[g], cnt, kNcclFloat64, g, nccl_comm_, s), "ncclBroadcast");
+    }
+    check(a.GroupEnd(), "ncclGroupEnd");
 }
 
 } // namespace las2

@@ -19,6 +19,9 @@ class Comm {
     int world() const { return world_; }
     // in-place sum over ranks, bit-identical result on every rank
     void allreduce_sum(double *buf, uint64_t n, cudaStream_t s);
+    // in-place all-gather of row ranges: rank g owns buf[offs[g] .. offs[g+1]) (offs has world()+1 entries, in doubles)
+    // and every rank ends up with all of them (one grouped broadcast per owner: exact counts, no staging)
+    void allgather_ranges(double *buf, const uint64_t *offs, cudaStream_t s);
 
   private:
     Comm() = default;

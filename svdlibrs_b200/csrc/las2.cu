@@ -63,6 +63,7 @@ struct Solver {
     // host (WorkSpace arrays, src/lib.rs:770-775)
     std::vector<double> alf, bet, eta, oldeta, ritz, bnd, w5;
     svdlas2_profile prof;
+    u64 n_sharded_sweeps = 0; // purge / restart sweeps whose rows were split over the ranks
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> opb_events;
     // result buffers (pinned, from the host pool) are acquired on a helper thread while the GPU runs lanso
     cudaStream_t copy_stream = nullptr;
@@ -166,7 +167,7 @@ struct Solver {
         if (step > 0) {
             // w0 -= (w3 . q_i) q_i with w3 the frozen copy: classical GS against all stored vectors, :1132-1135
             panel_cgs2(Q.get(), ld, N, 0, (u32)step, r.get(), nullptr, pw, &slot[1], &slot[2], nullptr, s,
-                       &prof.n_kernel_launches);
+                       &prof.n_kernel_launches, nullptr, nullptr, nullptr, op.comm, &n_sharded_sweeps);
             // make sure q[step] is orthogonal to q[step-1], :1138
             vec_dot(q(step - 1), r.get(), ld, slot[3], s);
             vec_axpy_dot(r.get(), q(step - 1), sum_of(3), nullptr, ld, slot[4], s);
@@ -227,7 +228,7 @@ struct Solver {
             if (*rnm > tol) {
                 // c = Q'[q r] against the frozen pair, [q r] -= Q c, then t = r . q (new), :1374-1384
                 panel_cgs2(Q.get(), ld, N, (u32)ll, (u32)(step - ll), q(step), r.get(), pw, &slot[0], &slot[1],
-                           &slot[2], s, &prof.n_kernel_launches);
+                           &slot[2], s, &prof.n_kernel_launches, nullptr, nullptr, nullptr, op.comm, &n_sharded_sweeps);
                 vec_axpy_dot(r.get(), q(step), sum_of(2), nullptr, ld, slot[3], s); // r -= t q ; |r|^2, :1386-1388
                 prof.n_kernel_launches += 1;
                 double v[4];
@@ -569,6 +570,9 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
     const double tl0 = wall();
     const u64 steps = sv.lanso(end_interval, random_seed, &neig);
     sv.prof.t_lanczos = wall() - tl0;
+    if (std::getenv("SVDLAS2_TRACE") && op.comm)
+        fprintf(stderr, "[svdlas2] lanso: %llu purge passes, %llu reorthogonalisation sweeps split over %d ranks\n",
+                (unsigned long long)sv.prof.n_purge_passes, (unsigned long long)sv.n_sharded_sweeps, op.comm->world());
 
     kappa = std::max(std::fabs(kappa), eps34()); // :627
     dg.kappa = kappa;

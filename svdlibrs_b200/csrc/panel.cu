@@ -9,6 +9,12 @@
 //  * ritz_contract: the Ritz back-transform V = Q Z_sel of ritvec (:1807-1817) on the FP64 FMA pipe.
 #include "vecops.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "comm.hpp"
+
 namespace las2 {
 
 namespace {
@@ -21,10 +27,10 @@ constexpr int kPanelWarps = kPanelThreads / 32;
 template <int NRHS>
 __global__ void __launch_bounds__(kPanelThreads)
 k_panel_dots(const double *__restrict__ Q, u64 ld, u32 col0, u32 ncols, const double *__restrict__ a,
-             const double *__restrict__ b, double *__restrict__ partials) {
+             const double *__restrict__ b, double *__restrict__ partials, u32 rb0) {
     __shared__ __align__(16) double sa[kPanelRows];
     __shared__ __align__(16) double sb[NRHS > 1 ? kPanelRows : 2];
-    const u64 row0 = (u64)blockIdx.x * kPanelRows;
+    const u64 row0 = (u64)(blockIdx.x + rb0) * kPanelRows; // rb0: first row block of this rank's share
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kPanelRows; i += kPanelThreads) {
         const u64 r = row0 + i;
@@ -93,11 +99,11 @@ constexpr int kUpdChunk = 512; // coefficients staged per pass
 template <int NRHS>
 __global__ void __launch_bounds__(kUpdThreads)
 k_panel_update(const double *__restrict__ Q, u64 ld, u32 col0, u32 ncols, const double *__restrict__ coeffs,
-               double *__restrict__ a, double *__restrict__ b, double *__restrict__ dot_parts) {
+               double *__restrict__ a, double *__restrict__ b, double *__restrict__ dot_parts, u64 i0, u64 i1) {
     __shared__ double sc[NRHS][kUpdChunk];
     __shared__ double sm[kUpdThreads / 32];
-    const u64 i = (u64)blockIdx.x * kUpdThreads + threadIdx.x; // double2 index
-    const bool live = i < ld / 2;
+    const u64 i = i0 + (u64)blockIdx.x * kUpdThreads + threadIdx.x; // double2 index inside this rank's share [i0, i1)
+    const bool live = i < i1;
     double2 av = make_double2(0.0, 0.0), bv = make_double2(0.0, 0.0);
     if (live) {
         av = reinterpret_cast<double2 *>(a)[i];
@@ -141,6 +147,25 @@ k_panel_update(const double *__restrict__ Q, u64 ld, u32 col0, u32 ncols, const 
         if (lane == 0) sm[warp] = acc;
         __syncthreads();
         if (threadIdx.x == 0) dot_parts[blockIdx.x] = ((sm[0] + sm[1]) + sm[2]) + sm[3];
+    }
+}
+
+// abs_a[cta] / abs_b[cta] = sum |coeff| over the CTA's 128 columns (sharded sweep: the coefficients are complete only
+// after the all-reduce, so the sums cannot come out of k_panel_reduce)
+template <int NRHS>
+__global__ void __launch_bounds__(128)
+k_coeff_abs(const double *__restrict__ coeffs, u32 ncols, double *__restrict__ abs_a, double *__restrict__ abs_b) {
+    __shared__ double sm[2][4];
+    const u32 c = blockIdx.x * 128 + threadIdx.x;
+    const double ca = c < ncols ? coeffs[c] : 0.0;
+    const double cb = (NRHS > 1 && c < ncols) ? coeffs[ncols + c] : 0.0;
+    double va = warp_sum(fabs(ca)), vb = warp_sum(fabs(cb));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sm[0][warp] = va; sm[1][warp] = vb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        abs_a[blockIdx.x] = ((sm[0][0] + sm[0][1]) + sm[0][2]) + sm[0][3];
+        abs_b[blockIdx.x] = ((sm[1][0] + sm[1][1]) + sm[1][2]) + sm[1][3];
     }
 }
 
@@ -202,38 +227,75 @@ k_ritz_contract(const double *__restrict__ Q, u64 ld, u32 js, const double *__re
 } // namespace
 
 void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, double *b, PanelWork &work,
-                PartialSlot *abs_a, PartialSlot *abs_b, PartialSlot *dot_out, cudaStream_t s, u64 *launches) {
+                PartialSlot *abs_a, PartialSlot *abs_b, PartialSlot *dot_out, cudaStream_t s, u64 *launches,
+                cudaEvent_t ev_begin, cudaEvent_t ev_mid, cudaEvent_t ev_end, Comm *comm, u64 *sharded_sweeps) {
     (void)n;
     if (ncols == 0) return;
-    const u32 nblocks = cdiv(ld, kPanelRows);
+    const u32 nblocks_all = cdiv(ld, kPanelRows);
+    // split the rows over the ranks when the sweep is big enough (same decision on every rank: sizes and environment only)
+    static const double shard_mb = [] { const char *e = std::getenv("SVDLAS2_SHARD_PURGE_MB"); return e ? std::atof(e) : 512.0; }();
+    const int G = comm ? comm->world() : 1;
+    const bool shard = G > 1 && nblocks_all >= (u32)G && 2.0 * ncols * (double)ld * 8.0 >= shard_mb * 1048576.0;
+    u32 rb0 = 0, rb1 = nblocks_all;
+    std::vector<u64> offs;
+    if (shard) {
+        const int g = comm->rank();
+        rb0 = (u32)((u64)nblocks_all * g / G);
+        rb1 = (u32)((u64)nblocks_all * (g + 1) / G);
+        offs.resize(G + 1);
+        for (int k = 0; k <= G; k++) offs[k] = std::min<u64>((u64)nblocks_all * k / G * kPanelRows, ld);
+        if (sharded_sweeps) *sharded_sweeps += 1;
+    }
+    const u32 nblocks = rb1 - rb0;
+    const u64 row_lo = std::min<u64>((u64)rb0 * kPanelRows, ld), row_hi = std::min<u64>((u64)rb1 * kPanelRows, ld);
+    const u64 i0 = row_lo / 2, i1 = row_hi / 2; // double2 units (ld and the block size are even)
     if (work.cap_cols < ncols || work.cap_blocks < nblocks) {
         size_t cc = work.cap_cols < ncols ? (size_t)ncols * 2 : work.cap_cols;
-        work.partials.alloc((size_t)nblocks * cc * 2);
+        size_t cb = std::max<size_t>(work.cap_blocks, nblocks);
+        work.partials.alloc(cb * cc * 2);
         work.coeffs.alloc(cc * 2);
         work.cap_cols = cc;
-        work.cap_blocks = nblocks;
+        work.cap_blocks = cb;
     }
-    u32 cs = cdiv(kMaxParts, nblocks);
+    u32 cs = cdiv(kMaxParts, std::max(1u, nblocks));
     const u32 max_cs = cdiv(ncols, kPanelWarps);
     if (cs > max_cs) cs = max_cs;
     if (cs < 1) cs = 1;
     const u32 nred = cdiv(ncols, 128);
     if (nred > (u32)kMaxParts) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "panel_cgs2: too many columns");
     dim3 grid(nblocks, cs);
-    const u32 ugrid = cdiv(ld / 2, kUpdThreads);
+    const u32 ugrid = cdiv(i1 - i0, kUpdThreads);
+    const int nrhs = b ? 2 : 1;
+    if (ev_begin) LAS2_CUDA(cudaEventRecord(ev_begin, s)); // tuning hook (svdlas2_test_time_panel)
+    // ---- coefficients ----
     if (b) {
-        k_panel_dots<2><<<grid, kPanelThreads, 0, s>>>(Q, ld, col0, ncols, a, b, work.partials);
+        k_panel_dots<2><<<grid, kPanelThreads, 0, s>>>(Q, ld, col0, ncols, a, b, work.partials, rb0);
         k_panel_reduce<2><<<nred, 128, 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
-        abs_a->nparts = abs_b->nparts = (int)nred;
-        // dot partials: one per update CTA, folded to <= kMaxParts
-        double *dp = dot_out ? dot_out->parts : nullptr;
-        if (dot_out && ugrid > (u32)kMaxParts) {
+    } else {
+        k_panel_dots<1><<<grid, kPanelThreads, 0, s>>>(Q, ld, col0, ncols, a, nullptr, work.partials, rb0);
+        k_panel_reduce<1><<<nred, 128, 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
+    }
+    if (launches) *launches += 2;
+    if (shard) {
+        comm->allreduce_sum(work.coeffs, (u64)nrhs * ncols, s);
+        if (b) k_coeff_abs<2><<<nred, 128, 0, s>>>(work.coeffs, ncols, abs_a->parts, abs_b->parts);
+        else k_coeff_abs<1><<<nred, 128, 0, s>>>(work.coeffs, ncols, abs_a->parts, abs_b->parts);
+        if (launches) *launches += 1;
+    }
+    abs_a->nparts = abs_b->nparts = (int)nred;
+    if (ev_mid) LAS2_CUDA(cudaEventRecord(ev_mid, s));
+    // ---- update ----
+    if (b) {
+        // dot partials: one per update CTA, folded to <= kMaxParts (replicated sweep only; a sharded sweep takes the
+        // dot product of the re-assembled pair instead)
+        double *dp = (dot_out && !shard) ? dot_out->parts : nullptr;
+        if (dot_out && !shard && ugrid > (u32)kMaxParts) {
             if (work.dotparts.size() < ugrid) work.dotparts.alloc(ugrid);
             dp = work.dotparts;
         }
-        k_panel_update<2><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, b, dp);
-        if (launches) *launches += 3;
-        if (dot_out) {
+        if (ugrid) k_panel_update<2><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, b, dp, i0, i1);
+        if (launches) *launches += 1;
+        if (dot_out && !shard) {
             if (ugrid > (u32)kMaxParts) {
                 const u32 group = cdiv(ugrid, kMaxParts);
                 const u32 ng = cdiv(ugrid, group);
@@ -245,12 +307,18 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
             }
         }
     } else {
-        k_panel_dots<1><<<grid, kPanelThreads, 0, s>>>(Q, ld, col0, ncols, a, nullptr, work.partials);
-        k_panel_reduce<1><<<nred, 128, 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
-        abs_a->nparts = abs_b->nparts = (int)nred;
-        k_panel_update<1><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, nullptr, nullptr);
-        if (launches) *launches += 3;
+        if (ugrid) k_panel_update<1><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, nullptr, nullptr, i0, i1);
+        if (launches) *launches += 1;
     }
+    if (shard) {
+        comm->allgather_ranges(a, offs.data(), s);
+        if (b) comm->allgather_ranges(b, offs.data(), s);
+        if (b && dot_out) {
+            vec_dot(a, b, ld, *dot_out, s);
+            if (launches) *launches += 1;
+        }
+    }
+    if (ev_end) LAS2_CUDA(cudaEventRecord(ev_end, s));
     LAS2_LAUNCH_CHECK();
 }
 

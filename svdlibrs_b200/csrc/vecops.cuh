@@ -67,8 +67,15 @@ struct PanelWork {
     size_t cap_cols = 0, cap_blocks = 0;
 };
 // abs_a / abs_b receive the partials of sum|ca| / sum|cb| ; dot_out (optional, needs b) those of a . b.
+// With a communicator (replicated panel, sharded operator) and a sweep big enough to pay for two small collectives,
+// the ROWS of the sweep are split over the ranks: every rank forms the coefficient partials of
+// its row blocks, one all-reduce of 2*ncols doubles completes them, every rank updates its rows of (a, b) and one
+// all-gather hands everybody the whole pair again -- bit-identical on all ranks, 1/G of the panel traffic each.
+class Comm;
 void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, double *b, PanelWork &work,
-                PartialSlot *abs_a, PartialSlot *abs_b, PartialSlot *dot_out, cudaStream_t s, u64 *launches);
+                PartialSlot *abs_a, PartialSlot *abs_b, PartialSlot *dot_out, cudaStream_t s, u64 *launches,
+                cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_mid = nullptr, cudaEvent_t ev_end = nullptr,
+                Comm *comm = nullptr, u64 *sharded_sweeps = nullptr);
 
 // Ritz back-transform (ritvec, src/lib.rs:1807-1817): V[:, c] = sum_k Q[:, k] * C[k, c], k < js, c < d.
 // C is js x d row-major on the device; V is column-major with leading dimension ld (each Ritz vector contiguous).

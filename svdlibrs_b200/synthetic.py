@@ -63,9 +63,11 @@ def powerlaw_csr(nrows: int, ncols: int, nnz: int, seed: int = 12345, alpha_rows
     indptr = [np.zeros(1, dtype=np.int64)]
     idx_chunks, val_chunks = [], []
     base = 0
-    for c0 in range(lo, hi, chunk_rows):
-        c1 = min(hi, c0 + chunk_rows)
-        rng = np.random.default_rng([seed, 2, c0])  # per-chunk stream: shards reproduce the same rows
+    # chunks are aligned to multiples of chunk_rows of the WHOLE matrix and each has its own random stream, so any
+    # row range reproduces exactly the rows of the full matrix (a partial chunk is generated whole and trimmed)
+    for c0 in range(lo // chunk_rows * chunk_rows, hi, chunk_rows):
+        c1 = min(nrows, c0 + chunk_rows)
+        rng = np.random.default_rng([seed, 2, c0])
         ln = lens[c0:c1]
         r = np.repeat(np.arange(c1 - c0, dtype=np.int64), ln)
         c = np.searchsorted(cdf, rng.random(r.size), side="right").astype(np.int64)
@@ -73,7 +75,11 @@ def powerlaw_csr(nrows: int, ncols: int, nnz: int, seed: int = 12345, alpha_rows
         v = np.log1p(rng.geometric(0.5, size=r.size).astype(np.float64))
         key, first = np.unique(r * ncols + c, return_index=True)
         r, c, v = key // ncols, key % ncols, v[first]
-        counts = np.bincount(r, minlength=c1 - c0)
+        a0, a1 = max(lo, c0) - c0, min(hi, c1) - c0  # rows of this chunk that belong to [lo, hi)
+        if a0 > 0 or a1 < c1 - c0:
+            keep = (r >= a0) & (r < a1)
+            r, c, v = r[keep] - a0, c[keep], v[keep]
+        counts = np.bincount(r, minlength=a1 - a0)
         indptr.append(base + np.cumsum(counts))
         base += int(counts.sum())
         idx_chunks.append(c)

@@ -28,16 +28,27 @@ def free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("shard_purge_mb", ["", "0"])
 @pytest.mark.parametrize("workload,scale,dims", [("cfg2", 0.05, 30), ("cfg3", 0.01, 20)])
-def test_sharded_solve_matches_single_gpu_and_oracle(workload, scale, dims):
+def test_sharded_solve_matches_single_gpu_and_oracle(workload, scale, dims, shard_purge_mb, monkeypatch):
+    """shard_purge_mb = "0": every reorthogonalisation sweep is split by rows over the ranks (all-reduce of the
+    coefficients + all-gather of the updated pair) instead of only the big ones"""
     if n_gpus() < 2:
         pytest.skip("needs at least 2 GPUs")
+    if shard_purge_mb:
+        monkeypatch.setenv("SVDLAS2_SHARD_PURGE_MB", shard_purge_mb)
+        monkeypatch.setenv("SVDLAS2_TRACE", "1")
     world = min(n_gpus(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py"),
            "--workload", workload, "--scale", str(scale), "--dims", str(dims), "--oracle", "1"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-3000:]
+    if shard_purge_mb:
+        import re
+        m = re.findall(r"(\d+) purge passes, (\d+) reorthogonalisation sweeps split", p.stderr)
+        # (cfg3 at this scale has N = 2000 < one 2048-row block per rank: nothing to split, the replicated path runs)
+        assert m and all(int(a) > 0 and (int(b) >= int(a) or workload == "cfg3") for a, b in m), p.stderr[-2000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("MULTI ")][-1]
     r = json.loads(line[len("MULTI "):])
     assert r["all_ranks_identical"]
