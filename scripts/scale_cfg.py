@@ -49,6 +49,7 @@ def vmax(x):
 t0 = time.time()
 with las2.ShardedOperator(Bl, nrows, lo, nnz_global, comm, False, device=local) as op:
     upload_s = vmax(time.time() - t0)
+    op.set("nside_on_rank0_only", 1)  # V is replicated: only rank 0 brings it to the host (U comes out row-sliced per rank)
     del Bl
     recs = []
     for i in range(a.solves):

@@ -296,6 +296,7 @@ int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value)
     Operator *op = reinterpret_cast<Operator *>(op_);
     if (!op || !knob) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
     if (!std::strcmp(knob, "profile")) { op->profile = value != 0; return SVDLAS2_OK; }
+    if (!std::strcmp(knob, "nside_on_rank0_only")) { op->nside_on_rank0_only = value != 0; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_variant")) { g_spmv_variant = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_hot")) { g_spmv_hot_entries = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_tma")) { g_spmv_tma = (int)value; return SVDLAS2_OK; }

@@ -20,13 +20,15 @@ class Comm {
     // in-place sum over ranks, bit-identical result on every rank
     void allreduce_sum(double *buf, uint64_t n, cudaStream_t s);
     // in-place all-gather of row ranges: rank g owns buf[offs[g] .. offs[g+1]) (offs has world()+1 entries, in doubles)
-    // and every rank ends up with all of them (one grouped broadcast per owner: exact counts, no staging)
+    // and every rank ends up with all of them (one ncclAllGather through an internal staging buffer)
     void allgather_ranges(double *buf, const uint64_t *offs, cudaStream_t s);
 
   private:
     Comm() = default;
     int rank_ = 0, world_ = 1;
     void *nccl_comm_ = nullptr;
+    void *stage_ = nullptr; // all-gather staging (world * largest range doubles)
+    uint64_t stage_cap_ = 0;
 };
 
 } // namespace las2

@@ -88,7 +88,8 @@ struct Solver {
         const u64 want = dims * (M + N) * sizeof(double);
         if (want <= host_prefetch_limit() && !std::getenv("SVDLAS2_NO_PREFETCH")) { // only when the upper bound d <= dims is affordable
             const int dev = op.device;
-            const size_t bm = std::max<u64>(1, dims * M) * sizeof(double), bn = std::max<u64>(1, dims * N) * sizeof(double);
+            const bool skip_n = op.comm && op.nside_on_rank0_only && op.comm->rank() != 0;
+            const size_t bm = std::max<u64>(1, dims * M) * sizeof(double), bn = std::max<u64>(1, skip_n ? 0 : dims * N) * sizeof(double);
             fut_m = std::async(std::launch::async, [dev, bm] { cudaSetDevice(dev); return host_acquire(bm); });
             fut_n = std::async(std::launch::async, [dev, bn] { cudaSetDevice(dev); return host_acquire(bn); });
             prefetched = true;
@@ -409,7 +410,11 @@ struct Solver {
         res->diagnostics.significant_values = d;   // sic, :648
         res->diagnostics.singular_values = nsig;   // sic, :649
 
-        const u64 mcols = M, ncols = N;
+        const u64 mcols = M;
+        // the N-side vectors are replicated over the ranks of a sharded run: on request only rank 0 downloads them
+        // (the other ranks return an N-side array of zero columns)
+        const bool skip_n = op.comm && op.nside_on_rank0_only && op.comm->rank() != 0;
+        const u64 ncols = skip_n ? 0 : N;
         const bool trace = std::getenv("SVDLAS2_TRACE") != nullptr;
         const double ta0 = wall();
         double *hU = (double *)(prefetched ? fut_m.get() : host_acquire(std::max<u64>(1, d * mcols) * sizeof(double)));
@@ -458,8 +463,9 @@ struct Solver {
         struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } evdel{ev};
         LAS2_CUDA(cudaEventRecord(ev, s));
         LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
-        LAS2_CUDA(cudaMemcpy2DAsync(hV, ncols * sizeof(double), V.get(), ld * sizeof(double), ncols * sizeof(double), d,
-                                    cudaMemcpyDeviceToHost, copy_stream));
+        if (ncols)
+            LAS2_CUDA(cudaMemcpy2DAsync(hV, ncols * sizeof(double), V.get(), ld * sizeof(double), ncols * sizeof(double), d,
+                                        cudaMemcpyDeviceToHost, copy_stream));
         DevBuf<double> U((size_t)d * mcols);
         DevBuf<double> S(d);
         DevBuf<double> nrm2(d); // |B_g v_i|^2 per triplet (summed over ranks when sharded)

@@ -30,6 +30,7 @@ struct Operator {
     DevBuf<char> l2_flush;
     // knobs
     bool profile = false;
+    bool nside_on_rank0_only = false; // sharded runs: ranks > 0 skip the download of the replicated N-side vectors
     // bookkeeping
     UploadStats upload;
     double t_upload = 0.0;
