@@ -174,8 +174,8 @@ SVDLAS2_API int svdlas2_operator_time_opb(svdlas2_operator *op, int reps, int fl
 /* knobs: "profile" (0/1: per-opb CUDA events); "nside_on_rank0_only" (0/1, sharded operators: the N-side singular
  * vectors are replicated over the ranks, so on request only rank 0 downloads them and the other ranks return an
  * N-side array of zero columns; the M-side vectors always come out row-sliced per rank); tuning / test overrides
- * of the SpMV: "spmv_variant" (-1 auto, 5 = warp-chunk stream, 0..4 = the older tile kernels), "spmv_hot",
- * "spmv_shape", "spmv_pdl", "spmv_carveout", "spmv_smem_pad_kb", "spmv_tma" */
+ * of the SpMV: "spmv_variant" (-1 auto, 5 = warp-chunk stream, 0..3 = the tile kernels on the natural CSR arrays),
+ * "spmv_hot", "spmv_shape", "spmv_pdl", "spmv_carveout", "spmv_smem_pad_kb" */
 SVDLAS2_API int svdlas2_operator_set(svdlas2_operator *op, const char *knob, int64_t value);
 
 /* ---- multi-GPU, one process per GPU (rows of the oriented operator B sharded by nnz) -- */

@@ -299,7 +299,6 @@ int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value)
     if (!std::strcmp(knob, "nside_on_rank0_only")) { op->nside_on_rank0_only = value != 0; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_variant")) { g_spmv_variant = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_hot")) { g_spmv_hot_entries = (int)value; return SVDLAS2_OK; }
-    if (!std::strcmp(knob, "spmv_tma")) { g_spmv_tma = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_smem_pad_kb")) { g_chunk_smem_pad_kb = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_pdl")) { g_chunk_pdl = (int)value; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "spmv_shape")) { g_chunk_shape = (int)value; return SVDLAS2_OK; }

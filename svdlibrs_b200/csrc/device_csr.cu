@@ -432,7 +432,7 @@ void transpose_csr(const DeviceCsr &X, DeviceCsr &XT, cudaStream_t s, UploadStat
 
 } // namespace
 
-// helpers shared with blocked_csr.cu
+// helpers shared with chunk_spmv.cu
 void exclusive_scan_u32(u32 *data, u64 n, cudaStream_t s, UploadStats &st) { exclusive_scan(data, n, s, st); }
 void expand_row_ids(const u32 *off, u32 rows, u64 nnz, u32 *rowid, cudaStream_t s, UploadStats &st) {
     if (nnz == 0) return;
@@ -442,25 +442,11 @@ void expand_row_ids(const u32 *off, u32 rows, u64 nnz, u32 *rowid, cudaStream_t 
     LAS2_LAUNCH_CHECK();
     st.launches++;
 }
-void build_tile_rows(const u32 *off, u32 rows, u64 nnz, u32 num_tiles, u32 tile, u32 *tile_row, cudaStream_t s, UploadStats &st) {
-    k_tile_rows<<<cdiv(num_tiles + 1, 256), 256, 0, s>>>(off, rows, nnz, num_tiles, tile, tile_row);
-    LAS2_LAUNCH_CHECK();
-    st.launches++;
-}
-void build_fix_list(const u32 *off, const u32 *tile_row, u32 num_tiles, u32 tile, u32 *fix_row, u32 *fix_first,
-                    cudaStream_t s, UploadStats &st) {
-    k_fix_list<<<cdiv(num_tiles, 256), 256, 0, s>>>(off, tile_row, num_tiles, tile, fix_row, fix_first);
-    LAS2_LAUNCH_CHECK();
-    st.launches++;
-}
-void build_blocked(DeviceCsr &X, cudaStream_t s, UploadStats &st); // blocked_csr.cu
 void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st); // chunk_spmv.cu
 
-// the SpMV-ready copies of a finished CSR matrix: the warp-chunk stream, else (opt-in / fallback) the older tile stream
-static void build_streams(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
-    build_chunk_stream(X, s, st);
-    if (!X.chk.active) build_blocked(X, s, st);
-}
+// the SpMV-ready copy of a finished CSR matrix: the warp-chunk stream (large matrices; small ones and matrices beyond
+// its index range run the tile kernels on the natural CSR arrays)
+static void build_streams(DeviceCsr &X, cudaStream_t s, UploadStats &st) { build_chunk_stream(X, s, st); }
 
 void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, const u64 *indices, const double *values,
                              cudaStream_t s, DeviceCsr &X, DeviceCsr &XT, UploadStats &st) {

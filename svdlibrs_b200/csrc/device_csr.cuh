@@ -14,38 +14,6 @@ constexpr u32 kSpmvTile = 2048;
 // candidate size of the shared-memory prefix of the gathered vector (64 KB of doubles)
 constexpr u32 kHotPrefix = 8192;
 
-// Column-blocked copy of a CSR matrix for the shared-memory-gather SpMV (blocked_csr.cu, spmv.cu):
-//   the columns are cut into blocks of kBlockWidth (2^14, so a local column index fits 16 bits and the
-//   matching slice of the gathered vector fits 128 KB of shared memory).  The first `nbk` blocks (those dense
-//   enough to pay for their per-row bookkeeping) become "slabs": slab s holds, row by row, the entries of all
-//   rows whose column lies in block s.  Entries of the remaining blocks form one more slab that keeps 32-bit
-//   column indices and is gathered through L1/L2.  A "virtual row" is (slab, row); the SpMV writes one partial
-//   sum per virtual row and a reduce kernel adds the slabs of a row in slab order (deterministic).
-constexpr u32 kBlockWidth = 16384;
-constexpr u32 kBlkTile = 1024; // non-zeros per tile of the blocked stream (one TMA stage: 8 KB values + 2/4 KB indices)
-
-struct BlockedCsr {
-    bool active = false;
-    u32 nbk = 0;        // slabs with shared-memory gathers (blocks 0 .. nbk-1)
-    u32 nslabs = 0;     // nbk (+1 when a remainder slab exists)
-    bool has_rem = false;
-    u64 rows = 0, cols = 0;
-    u64 vrows = 0;      // nslabs * rows
-    u64 padded = 0;     // length of the slab-ordered, tile-padded non-zero stream
-    u64 rem_start = 0;  // stream position where the remainder slab begins (multiple of the tile)
-    u32 num_tiles = 0, blocked_tiles = 0;
-    DevBuf<u32> voff;        // vrows + 1 positions into the stream
-    DevBuf<double> val;      // padded
-    DevBuf<uint16_t> idx16;  // rem_start local column indices
-    DevBuf<u32> idx32;       // padded - rem_start global column indices
-    DevBuf<u32> tile_row;    // num_tiles + 1 (virtual rows)
-    DevBuf<u32> slab_tile_start; // nslabs + 1
-    DevBuf<double> carry, head;  // num_tiles
-    DevBuf<u32> fix_row, fix_first; // num_tiles: row completed by the fix-up of tile b (or ~0u) and its first tile
-    DevBuf<double> partial;      // vrows (unused when nslabs == 1)
-    u64 stream_bytes = 0;        // bytes one SpMV actually moves (for reporting)
-};
-
 // Warp-chunk stream (chunk_spmv.cu): the row-ordered non-zeros cut into chunks of 256, one warp per chunk.  A
 // chunk is 3072 contiguous bytes, fetched by ONE bulk copy: 4 x 32 x 16 B of values, then 2 x 32 x 16 B of
 // column indices, arranged so that six conflict-free 128-bit shared-memory reads hand lane l the 8 CONSECUTIVE
@@ -86,7 +54,6 @@ struct ChunkStream {
 
 struct DeviceCsr {
     u64 rows = 0, cols = 0, nnz = 0;
-    BlockedCsr blk;
     ChunkStream chk;
     DevBuf<u32> off;    // rows + 1 row offsets
     DevBuf<u32> idx;    // padded_nnz column indices (padding: index 0)

@@ -5,7 +5,6 @@
 namespace las2 {
 
 extern int g_spmv_variant;     // -1 auto; test / tuning override (svdlas2_operator_set "spmv_variant")
-extern int g_spmv_tma;
 extern int g_chunk_carveout_pct;  // chunk_spmv.cu: explicit carve-out (percent of 228 KB), -1 = exact fit
 extern int g_chunk_pdl;           // chunk_spmv.cu: programmatic dependent launch on/off
 extern int g_chunk_shape;         // chunk_spmv.cu: 32 (warps) x 1 (stage) or 16 x 2

@@ -221,22 +221,20 @@ def test_iterations_and_kappa_parameters(las2, oracle):
     assert_svd_parity(got, ref)
 
 
-@pytest.mark.parametrize("variant,hot", [(0, -1), (1, -1), (2, -1), (3, 0), (3, 5), (3, 1000), (3, -1), (4, -1), (5, -1), (5, 0), (5, 7),
+@pytest.mark.parametrize("variant,hot", [(0, -1), (1, -1), (2, -1), (3, 0), (3, 5), (3, 1000), (3, -1),
                                          (6, -1), (6, 0), (6, 7), (6, 4096), (6, 8192), (7, -1)])
 def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
-    """all SpMV kernels (warp-chunk stream with several shared-memory prefix sizes, one-CTA-per-tile with 256/128/512
-    threads, persistent hot-prefix kernel, blocked/interleaved tile streams) on ragged + power-law inputs, both
-    orientations"""
+    """all SpMV kernels (warp-chunk stream with several shared-memory prefix sizes and in slab mode, one-CTA-per-tile
+    with 256/128/512 threads, persistent hot-prefix tile kernel) on ragged + power-law inputs, both orientations"""
     import os
     from svdlibrs_b200 import synthetic
-    # test variant -> (library variant, formats built at upload): 4 = slabs where they pay, 5 = tile stream without
-    # slabs, 6 = the warp-chunk stream (the default of large matrices, forced here at test size)
-    # (forced at test size); 7 = the same stream in slab mode (column blocks of 16384 gathered from shared memory)
+    # test variant -> library variant: 0..3 = the tile kernels on the natural CSR arrays; 6 = the warp-chunk stream (the
+    # default of large matrices, forced here at test size); 7 = the same stream in slab mode (column blocks of 16384
+    # gathered from shared memory)
     os.environ["SVDLAS2_SPMV"] = "chunk" if variant >= 6 else "tile"
     os.environ["SVDLAS2_SLABS"] = "1" if variant == 7 else "0"
-    os.environ["SVDLAS2_BLOCKED"] = {4: "1", 5: "2"}.get(variant, "0")
     slabs = variant == 7
-    variant = {5: 4, 6: 5, 7: 5}.get(variant, variant)
+    variant = {6: 5, 7: 5}.get(variant, variant)
     rng = np.random.default_rng(21)
     mats = [synthetic.make("cfg2", scale=0.01)[0],
             sp.random(3000, 5000, density=0.004, format="csr", random_state=rng)]
@@ -259,7 +257,6 @@ def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
             finally:
                 op.set("spmv_variant", -1)
                 op.set("spmv_hot", -1)
-                os.environ.pop("SVDLAS2_BLOCKED", None)
                 os.environ.pop("SVDLAS2_SPMV", None)
                 os.environ.pop("SVDLAS2_SLABS", None)
 
