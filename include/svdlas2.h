@@ -138,6 +138,12 @@ SVDLAS2_API const char *svdlas2_last_error(void);
 
 SVDLAS2_API int svdlas2_abi_version(void);
 
+/* The library keeps the result buffers it hands out (registered host memory) and its device scratch (the
+ * stream-ordered memory pool of the current device) cached between calls, because creating either costs more than
+ * a small solve.  This gives everything that is not in use back to the operating system / the driver -- e.g. before
+ * another library in the same process needs the GPU's memory.  Returns 0. */
+SVDLAS2_API int svdlas2_trim_caches(void);
+
 /* ---- resident-operator entry points ------------------------------------------------------------- *
  * The same path split in two so a caller (an `impl SMat`, a benchmark, a parity test) can keep the
  * operator in HBM: create = the reference's implicit "borrow the matrix", solve = lanso + ritvec.       */

@@ -66,6 +66,8 @@ extern "C" {
         random_seed: u32, out: *mut *mut svdlas2_result) -> c_int;
     pub fn svdlas2_free(result: *mut svdlas2_result);
     pub fn svdlas2_last_error() -> *const c_char;
+    /// hands the library's cached result buffers and device scratch back (include/svdlas2.h)
+    pub fn svdlas2_trim_caches() -> c_int;
 }
 
 pub const CSR: OneShot = svdlas2_csr;

@@ -219,3 +219,9 @@ impl SMat for nalgebra_sparse::coo::CooMatrix<f64> {
         })
     }
 }
+
+/// Not part of the reference crate: gives the registered host buffers and the device scratch the CUDA library keeps
+/// cached between calls back to the operating system / the driver.
+pub fn trim_caches() {
+    unsafe { ffi::svdlas2_trim_caches() };
+}

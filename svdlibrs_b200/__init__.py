@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["svd", "svd_dim", "svd_dim_seed", "svdLAS2", "SvdRec", "Diagnostics", "SvdLibError", "Operator", "RawMatrix",
-           "ShardedOperator", "Communicator", "comm_unique_id", "build"]
+           "ShardedOperator", "Communicator", "comm_unique_id", "build", "trim_caches"]
 
 build = _lib.build
 
@@ -295,6 +295,11 @@ class Operator:
                     bytes_opb=24 * z + 20 * (m + n) + 8,
                     bytes_spmv_b=12 * z + 4 * (m + 1) + 8 * n + 8 * m,
                     bytes_spmv_bt=12 * z + 4 * (n + 1) + 8 * m + 8 * n)
+
+
+def trim_caches() -> None:
+    """Give the cached host result buffers and the cached device scratch back (see svdlas2_trim_caches)."""
+    _lib.lib().svdlas2_trim_caches()
 
 
 def comm_unique_id() -> bytes:

@@ -49,6 +49,7 @@ class Result(C.Structure):
 # every symbol include/svdlas2.h declares (tests/test_abi_symbols.py checks the header against this list)
 SYMBOLS = [
     "svdlas2_csr", "svdlas2_csc", "svdlas2_coo", "svdlas2_free", "svdlas2_last_error", "svdlas2_abi_version",
+    "svdlas2_trim_caches",
     "svdlas2_operator_create", "svdlas2_operator_destroy", "svdlas2_operator_solve", "svdlas2_operator_opa",
     "svdlas2_operator_opb", "svdlas2_operator_shape", "svdlas2_operator_time_opb", "svdlas2_operator_set",
     "svdlas2_comm_unique_id", "svdlas2_comm_create", "svdlas2_comm_destroy", "svdlas2_operator_create_shard",
@@ -88,6 +89,8 @@ def lib():
     L.svdlas2_last_error.argtypes = []
     L.svdlas2_last_error.restype = C.c_char_p
     L.svdlas2_abi_version.argtypes = []
+    L.svdlas2_trim_caches.argtypes = []
+    L.svdlas2_trim_caches.restype = C.c_int
     L.svdlas2_abi_version.restype = C.c_int
     OP = C.c_void_p
     L.svdlas2_operator_create.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p, f64p, C.c_int,

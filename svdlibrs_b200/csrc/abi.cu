@@ -115,6 +115,13 @@ extern "C" {
 
 int svdlas2_abi_version(void) { return SVDLAS2_ABI_VERSION; }
 
+int svdlas2_trim_caches(void) {
+    return guarded([&] {
+        host_pool_trim();
+        device_pool_trim();
+    });
+}
+
 const char *svdlas2_last_error(void) { return g_last_error.c_str(); }
 
 int svdlas2_csr(uint64_t nrows, uint64_t ncols, uint64_t nnz, const uint64_t *row_offsets, const uint64_t *col_indices,

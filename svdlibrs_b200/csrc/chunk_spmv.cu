@@ -505,7 +505,7 @@ k_chunk_fixup(const u32 *__restrict__ fix_row, const u32 *__restrict__ fix_first
     }
 }
 
-int g_chunk_carve[6] = {-2, -2, -2, -2, -2, -2}; // carve-out currently set on each instantiation
+int g_chunk_carve[kMaxDevicesTracked][6]; // carve-out (+1) currently set on each instantiation, per device (0 = not yet)
 
 } // namespace
 
@@ -725,11 +725,12 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
     // L1 lines their misses land in (scripts/micro/gather_l1_sweep.cu: 0.95 gathers/clk/SM with <= 132 KB carved
     // out, 0.43 with 228 KB).
     const int carve = g_chunk_carveout_pct >= 0 ? g_chunk_carveout_pct : (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1);
+    const int dev_slot = current_device_slot();
     auto configure = [&](const void *fn, int &cached) {
-        if (cached == carve) return;
+        if (cached == carve + 1) return;
         LAS2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         LAS2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        cached = carve;
+        cached = carve + 1;
     };
     // launch shape: 32 warps x 1 stage unless the knob "spmv_shape" says 16 x 2 (value 16)
     const bool wide = g_chunk_shape != 16;
@@ -741,7 +742,7 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
     if (mode != 2 && K.has_empty_rows) LAS2_CUDA(cudaMemsetAsync(y, 0, K.rows * sizeof(double), s));
 #define LAS2_CHUNK_LAUNCH(MODE, WARPS, STAGES, SLOT)                                                                   \
     do {                                                                                                               \
-        configure((const void *)k_spmv_chunk<MODE, WARPS, STAGES>, g_chunk_carve[SLOT]);                               \
+        configure((const void *)k_spmv_chunk<MODE, WARPS, STAGES>, g_chunk_carve[dev_slot][SLOT]);                               \
         launch_pdl(k_spmv_chunk<MODE, WARPS, STAGES>, dim3(grid), dim3(WARPS * 32), smem, s, (const uint4 *)K.data,       \
                    (const u32 *)K.chunk_row, rowmap, x, out, (double *)K.carry, (double *)K.head, K.num_chunks,          \
                    mode == 2 ? 0u : hot, (const u32 *)K.slab_chunk_start, K.nslabs, (u32)K.cols);                      \

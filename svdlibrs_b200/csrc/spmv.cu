@@ -264,7 +264,7 @@ int g_spmv_hot_entries = -1; // -1 auto
 namespace {
 constexpr u32 kHotMaxEntries = 16384; // upper bound of the knob: 128 KB of the 227 KB
 size_t hot_smem_bytes(u32 hot) { return sizeof(HotGroupSmem) * kHotGroups + (size_t)hot * sizeof(double); }
-bool g_hot_attr_set = false;
+bool g_hot_attr_set[kMaxDevicesTracked]; // per device
 } // namespace
 
 void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches); // chunk_spmv.cu
@@ -283,10 +283,11 @@ void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *l
         u32 hot = g_spmv_hot_entries >= 0 ? (u32)g_spmv_hot_entries : A.hot_entries;
         if (hot > kHotMaxEntries) hot = kHotMaxEntries;
         if (hot > A.cols) hot = (u32)A.cols;
-        if (!g_hot_attr_set) {
+        bool &attr_set = g_hot_attr_set[current_device_slot()];
+        if (!attr_set) {
             LAS2_CUDA(cudaFuncSetAttribute(k_spmv_hot, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)hot_smem_bytes(kHotMaxEntries)));
-            g_hot_attr_set = true;
+            attr_set = true;
         }
         u32 grid = kNumSMs;
         if (grid * kHotGroups > A.num_tiles) grid = cdiv(A.num_tiles, kHotGroups);

@@ -126,7 +126,8 @@ void ql_replay(const QlPlan &plan, u32 js, u32 ldz, double *zT, cudaStream_t s, 
         if (h2d_bytes) *h2d_bytes += plan.sweeps.size() * sizeof(QlSweep) + plan.sc.size() * sizeof(double);
         if (in_smem) {
             const size_t bytes = (size_t)js * rpc * sizeof(double);
-            static bool attr_set = false;
+            static bool attr_set_dev[kMaxDevicesTracked];
+            bool &attr_set = attr_set_dev[current_device_slot()];
             if (!attr_set) {
                 LAS2_CUDA(cudaFuncSetAttribute(k_ql_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 attr_set = true;

@@ -101,6 +101,15 @@ class PinnedBuf {
     size_t n_ = 0;
 };
 
+// Function attributes (dynamic shared-memory limit, carve-out) are per device: caches of "already set" are indexed by
+// the current device so that a process driving several GPUs configures every one of them.
+constexpr int kMaxDevicesTracked = 64;
+static inline int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevicesTracked) ? dev : 0;
+}
+
 static inline unsigned cdiv(u64 a, u64 b) { return (unsigned)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148; // B200: 2 dies x 74 SMs; grids are sized in multiples of this

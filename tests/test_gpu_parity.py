@@ -202,6 +202,30 @@ def test_cfg1_full_size_parity(las2, oracle):
     assert np.allclose(got.trace["bet"][1:k], ref.trace["bet"][1:k], rtol=1e-9)
 
 
+def test_trim_caches_keeps_the_library_usable(las2):
+    from svdlibrs_b200 import synthetic
+    A, _ = synthetic.make("cfg2", scale=0.01)
+    a = las2.svd_dim_seed(A, 10, 5)
+    las2.trim_caches()  # with a result still alive: its buffers must survive
+    b = las2.svd_dim_seed(A, 10, 5)
+    assert a == b
+    del a, b
+    las2.trim_caches()
+    assert las2.svd_dim_seed(A, 10, 5).d == 10
+
+
+def test_panel_timing_hook(las2):
+    """GPU tuning hook behind scripts/panel_bench.py"""
+    import ctypes as C
+    from svdlibrs_b200 import _lib
+    L = _lib.lib()
+    L.svdlas2_test_time_panel.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.svdlas2_test_time_panel.restype = C.c_int
+    d, u = C.c_double(), C.c_double()
+    assert L.svdlas2_test_time_panel(50_000, 40, 2, 0, C.byref(d), C.byref(u)) == 0
+    assert d.value > 0 and u.value > 0
+
+
 def test_operator_is_reusable_and_deterministic(las2):
     from svdlibrs_b200 import synthetic
     A, _ = synthetic.make("cfg2", scale=0.01)
@@ -242,9 +266,13 @@ def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
     rows = np.concatenate([np.full(l, i) for i, l in enumerate(lens)])
     cols = np.concatenate([np.sort(rng.choice(7000, size=l, replace=False)) for l in lens])
     mats.append(sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(400, 7000)))
-    if slabs:  # wide enough for several slabs in both orientations; short pieces (slow path) and empty pieces
-        mats.append(sp.random(30000, 50000, density=0.0004, format="csr", random_state=rng))
+    if slabs:  # wide enough for several slabs in both orientations; short pieces (slow path) and empty pieces; odd sizes
+        mats.append(sp.random(30001, 50001, density=0.0004, format="csr", random_state=rng))
         mats.append(synthetic.make("cfg3", scale=0.02)[0])
+        # a column block without any entry (slab 1 of 4) and an empty last slab in the other orientation
+        G = sp.random(20000, 50001, density=0.001, format="coo", random_state=rng)
+        keep = (G.col < 16000) | ((G.col >= 33000) & (G.col < 49000))
+        mats.append(sp.csr_matrix((G.data[keep], (G.row[keep], G.col[keep])), shape=G.shape))
     for A in mats:
         with las2.Operator(A) as op:
             op.set("spmv_variant", variant)
