@@ -126,10 +126,10 @@ def oracle_sample(A, dims: int, sample_iterations: int):
     return r, dt
 
 
-def pick_sample_iterations(nnz: int, dims: int) -> int:
-    # ~4 ns per nnz per opb on one host core: aim at ~10 s of opb work, at least dims steps
+def pick_sample_iterations(nnz: int, dims: int, seconds: float = 10.0) -> int:
+    # ~4 ns per nnz per opb on one host core: aim at `seconds` of opb work, at least dims steps
     per_opb = max(1e-4, 4.5e-9 * nnz)
-    return int(max(dims, min(4 * dims, 10.0 / per_opb)))
+    return int(max(dims, min(4 * dims, seconds / per_opb)))
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -138,7 +138,9 @@ def run_reference(args):
     if rank != 0:
         return
     A, dims, info = make_workload(args.workload, args.scale)
-    it = args.sample_iterations or pick_sample_iterations(A.nnz, dims)
+    # the whole --warmup W --steps K run is meant to end within a few minutes: ~150 s of CPU work shared by the steps
+    per_step_s = min(10.0, max(2.0, 150.0 / max(1, args.warmup + args.steps)))
+    it = args.sample_iterations or pick_sample_iterations(A.nnz, dims, per_step_s)
     it = min(it, min(A.shape))
     times, nopb = [], 0
     for i in range(args.warmup + args.steps):
@@ -355,7 +357,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", help="cfg1..cfg5 of BASELINE.json (default cfg2 = configs[1])")
