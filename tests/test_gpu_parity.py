@@ -202,6 +202,23 @@ def test_cfg1_full_size_parity(las2, oracle):
     assert np.allclose(got.trace["bet"][1:k], ref.trace["bet"][1:k], rtol=1e-9)
 
 
+def test_command_line_matches_the_api(las2, tmp_path, capsys):
+    """python -m svdlibrs_b200 matrix.mtx -d 3 -s 3141 -o prefix (loaders + CLI of SURVEY 8(f) rank 4)"""
+    import json
+    from svdlibrs_b200 import __main__ as cli, io as las2_io
+    m = tmp_path / "g.mtx"
+    rows, cols = np.nonzero(GOLDEN_M)
+    m.write_text("%%MatrixMarket matrix coordinate real general\n3 3 9\n" +
+                 "".join(f"{r + 1} {c + 1} {GOLDEN_M[r, c]!r}\n" for r, c in zip(rows, cols)))
+    assert cli.main([str(m), "-d", "3", "-s", "3141", "-o", str(tmp_path / "out")]) == 0
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["d"] == 3 and line["diagnostics"]["random_seed"] == 3141
+    ref = las2.svd_dim_seed(sp.coo_matrix(GOLDEN_M), 3, 3141)
+    assert np.array_equal(np.loadtxt(tmp_path / "out-Ut", skiprows=1), ref.ut)
+    assert np.array_equal(np.loadtxt(tmp_path / "out-Vt", skiprows=1), ref.vt)
+    assert np.array_equal(np.loadtxt(tmp_path / "out-S", skiprows=1), ref.s)
+
+
 def test_trim_caches_keeps_the_library_usable(las2):
     from svdlibrs_b200 import synthetic
     A, _ = synthetic.make("cfg2", scale=0.01)
