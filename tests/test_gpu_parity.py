@@ -209,7 +209,7 @@ def test_command_line_matches_the_api(las2, tmp_path, capsys):
     m = tmp_path / "g.mtx"
     rows, cols = np.nonzero(GOLDEN_M)
     m.write_text("%%MatrixMarket matrix coordinate real general\n3 3 9\n" +
-                 "".join(f"{r + 1} {c + 1} {GOLDEN_M[r, c]!r}\n" for r, c in zip(rows, cols)))
+                 "".join(f"{r + 1} {c + 1} {float(GOLDEN_M[r, c])!r}\n" for r, c in zip(rows, cols)))
     assert cli.main([str(m), "-d", "3", "-s", "3141", "-o", str(tmp_path / "out")]) == 0
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert line["d"] == 3 and line["diagnostics"]["random_seed"] == 3141
