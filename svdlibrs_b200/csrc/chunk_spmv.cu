@@ -10,16 +10,19 @@
 // Hence this design:
 //   * ONE WARP owns a chunk of 256 non-zeros end to end: no block barrier, no shared atomics, no row-offset loads.
 //     Row starts travel inside the stream (bit 31 of the column index); the only per-chunk metadata is one u32.
-//   * The chunk's 3072 bytes arrive by ONE bulk copy (cp.async.bulk + mbarrier) into the warp's own 2-deep ring,
-//     off the LSU path, so the tag stage is left to the gathers.  16 warps x 2 x 3 KB + the hot prefix of x
-//     (<= 32 KB) = 128 KB of shared memory, which keeps ~120 KB of L1 for gathers in flight.
+//   * The chunk's 3072 bytes arrive by ONE bulk copy (cp.async.bulk + mbarrier) into the warp's own stage, off the
+//     LSU path, so the tag stage is left to the gathers.  32 warps x 1 stage x 3 KB (96 KB; measured faster than
+//     16 warps x 2 stages: the kernel is latency-bound and the other 31 warps hide a warp's copy) + the hot prefix
+//     of x (<= 64 KB) stays <= 164 KB of shared memory, which keeps >= 90 KB of L1 for gathers in flight; the
+//     carve-out is set explicitly per launch.
 //   * Each lane multiplies its 8 CONSECUTIVE elements and sums them serially into (piece before its first row
 //     start, piece after); one warp-shuffle segmented scan stitches the lanes; rows that end inside the chunk are
 //     written straight to y, the piece open at the chunk's start / end goes to head[] / carry[] and
 //     k_chunk_fixup completes those rows in chunk order.  Every order is fixed by the data layout: deterministic.
 //   * Chunks in which some lane holds two or more row starts (rows shorter than 8) take a branchy variant of the
 //     per-lane step (marked at upload in bit 31 of chunk_row[]); everything else is shared.
-//   * Slab mode (MODE 2; chosen at upload when a (16384-column block, row) piece holds >= 4 entries on average): the
+//   * Slab mode (MODE 2; chosen at upload for matrices of >= 20 M nnz whose gathered vector has no popular prefix and
+//     whose (16384-column block, row) pieces hold >= 4 entries on average): the
 //     stream is ordered (slab, row, column) with local column indices, each CTA takes a contiguous range of chunks
 //     and keeps the slab's 128 KB slice of x in shared memory, so EVERY gather is an ld.shared (~0.33 wavefronts
 //     instead of one L1 line; profiles/r1f_spmv_ncu_summary.md shows the L1TEX pipe, not HBM, bounding MODE 0/1).
