@@ -441,11 +441,13 @@ struct Solver {
         DevBuf<double> C((size_t)js * d);
         ritz_coefficients(zT.get(), ldz, (u32)js, dphys.get(), (u32)d, C.get(), s, &prof.n_kernel_launches);
         DevBuf<double> V((size_t)d * ld);
-        ritz_contract(Q.get(), ld, N, (u32)js, C.get(), (u32)d, V.get(), s, &prof.n_kernel_launches);
+        bool ritz_sharded = false;
+        ritz_contract(Q.get(), ld, N, (u32)js, C.get(), (u32)d, V.get(), s, &prof.n_kernel_launches, op.comm, &ritz_sharded);
         LAS2_CUDA(cudaStreamSynchronize(s));
-        if (trace) fprintf(stderr, "[svdlas2] ritvec: contraction N=%llu js=%llu d=%llu in %.3f s (%.1f TFLOP/s)\n",
+        if (trace) fprintf(stderr, "[svdlas2] ritvec: contraction N=%llu js=%llu d=%llu in %.3f s (%.1f TFLOP/s)%s\n",
                            (unsigned long long)N, (unsigned long long)js, (unsigned long long)d, wall() - tc0,
-                           2.0 * (double)N * (double)js * (double)d / (wall() - tc0) / 1e12);
+                           2.0 * (double)N * (double)js * (double)d / (wall() - tc0) / 1e12,
+                           ritz_sharded ? ", rows split over the ranks" : "");
         const double tt0 = wall();
         zT.release();
         C.release();

@@ -187,11 +187,11 @@ constexpr int kRitzChunk = 256;
 
 __global__ void __launch_bounds__(kRitzThreads)
 k_ritz_contract(const double *__restrict__ Q, u64 ld, u32 js, const double *__restrict__ C, u32 d,
-                double *__restrict__ V) {
+                double *__restrict__ V, u64 i0, u64 i1) {
     __shared__ double sc[kRitzChunk][kRitzCols];
-    const u64 i = (u64)blockIdx.x * kRitzThreads + threadIdx.x; // double2 row index
+    const u64 i = i0 + (u64)blockIdx.x * kRitzThreads + threadIdx.x; // double2 row index inside this rank's share [i0, i1)
     const u32 c0 = blockIdx.y * kRitzCols;
-    const bool live = i < ld / 2;
+    const bool live = i < i1;
     double2 acc[kRitzCols];
 #pragma unroll
     for (int t = 0; t < kRitzCols; t++) acc[t] = make_double2(0.0, 0.0);
@@ -323,13 +323,35 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
 }
 
 void ritz_contract(const double *Q, u64 ld, u64 n, u32 js, const double *C, u32 d, double *V, cudaStream_t s,
-                   u64 *launches) {
+                   u64 *launches, Comm *comm, bool *sharded) {
     (void)n;
+    if (sharded) *sharded = false;
     if (d == 0 || js == 0) return;
-    dim3 grid(cdiv(ld / 2, kRitzThreads), cdiv(d, kRitzCols));
-    k_ritz_contract<<<grid, kRitzThreads, 0, s>>>(Q, ld, js, C, d, V);
-    LAS2_LAUNCH_CHECK();
-    if (launches) *launches += 1;
+    // Sharded runs hold the panel replicated: for a contraction big enough to matter every rank forms only its row blocks
+    // of V and one all-gather per Ritz vector completes them.  Each element is computed by exactly one rank with the
+    // arithmetic of the replicated kernel, so the result is bit-identical to the single-GPU one on every rank.
+    static const double shard_gflop = [] { const char *e = std::getenv("SVDLAS2_SHARD_RITZ_GFLOP"); return e ? std::atof(e) : 50.0; }();
+    const int G = comm ? comm->world() : 1;
+    const u32 nblocks_all = cdiv(ld, kPanelRows);
+    const bool shard = G > 1 && nblocks_all >= (u32)G && 2.0 * (double)ld * js * d >= shard_gflop * 1e9;
+    u64 i0 = 0, i1 = ld / 2;
+    std::vector<u64> offs;
+    if (shard) {
+        offs.resize(G + 1);
+        for (int k = 0; k <= G; k++) offs[k] = std::min<u64>((u64)nblocks_all * k / G * kPanelRows, ld);
+        i0 = offs[comm->rank()] / 2;
+        i1 = offs[comm->rank() + 1] / 2;
+    }
+    if (i1 > i0) {
+        dim3 grid(cdiv(i1 - i0, kRitzThreads), cdiv(d, kRitzCols));
+        k_ritz_contract<<<grid, kRitzThreads, 0, s>>>(Q, ld, js, C, d, V, i0, i1);
+        LAS2_LAUNCH_CHECK();
+        if (launches) *launches += 1;
+    }
+    if (shard) {
+        for (u32 c = 0; c < d; c++) comm->allgather_ranges(V + (u64)c * ld, offs.data(), s);
+        if (sharded) *sharded = true;
+    }
 }
 
 } // namespace las2

@@ -80,6 +80,6 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
 // Ritz back-transform (ritvec, src/lib.rs:1807-1817): V[:, c] = sum_k Q[:, k] * C[k, c], k < js, c < d.
 // C is js x d row-major on the device; V is column-major with leading dimension ld (each Ritz vector contiguous).
 void ritz_contract(const double *Q, u64 ld, u64 n, u32 js, const double *C, u32 d, double *V, cudaStream_t s,
-                   u64 *launches);
+                   u64 *launches, Comm *comm = nullptr, bool *sharded = nullptr);
 
 } // namespace las2
