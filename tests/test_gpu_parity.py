@@ -334,3 +334,31 @@ def test_cfg2_full_size_invariants(las2):
         assert np.linalg.norm(av - r.s[i] * r.ut[i]) <= 1e-9 * r.s[0]
         atu = A.T @ r.ut[i]
         assert np.linalg.norm(atu - r.s[i] * r.vt[i]) <= 1e-6 * r.s[0]   # Ritz residual: bounded by kappa-level accuracy
+
+
+def test_cfg3_full_size_invariants(las2):
+    """BASELINE configs[2] at FULL size (wide CSC 200k x 2M, ~9.1e7 nnz, dims 100: the internal-transpose path, slab mode
+    on the B' side) through size-independent properties: chunk-stream kernels agree with the tile kernel on the same
+    vector, repeat solves are bit-identical, ut / vt come back un-swapped with the right shapes, sigma descends, the
+    N-side vectors are orthonormal, A v = sigma u per triplet."""
+    from svdlibrs_b200 import synthetic
+    A, dims = synthetic.make("cfg3")
+    assert A.format == "csc" and A.shape == (200_000, 2_000_000)
+    rng = np.random.default_rng(2)
+    with las2.Operator(A) as op:
+        assert op.transposed
+        for transposed in (False, True):
+            x = rng.standard_normal(A.shape[0] if transposed else A.shape[1])
+            op.set("spmv_variant", 2)
+            ref = op.opa(x, transposed)
+            op.set("spmv_variant", -1)
+            y = op.opa(x, transposed)
+            assert not np.isnan(y).any() and np.abs(y - ref).max() <= 1e-11 * np.abs(ref).max()
+        r = op.solve(dims, random_seed=12345)
+        r2 = op.solve(dims, random_seed=12345)
+    assert r == r2
+    assert r.diagnostics.transposed and r.ut.shape == (dims, A.shape[0]) and r.vt.shape == (dims, A.shape[1])
+    assert r.d == dims and np.all(np.diff(r.s) <= 0)
+    assert orthonormality_defect(r.ut) < 1e-8  # rows(A) = 200k is the N side of the transposed operator
+    for i in (0, dims // 2, dims - 1):
+        assert np.linalg.norm(A.T @ r.ut[i] - r.s[i] * r.vt[i]) <= 1e-9 * r.s[0]
