@@ -158,7 +158,9 @@ SVDLAS2_API int svdlas2_operator_create(int format, uint64_t nrows, uint64_t nco
                             const uint64_t *b, const double *values, int device, svdlas2_operator **op);
 SVDLAS2_API void svdlas2_operator_destroy(svdlas2_operator *op);
 
-/* svdLAS2 (src/lib.rs:570-655) on a resident operator. */
+/* svdLAS2 (src/lib.rs:570-655) on a resident operator.  random_seed == 0 draws a seed from OS entropy like the
+ * reference (:578-581) and reports it in Diagnostics; on a sharded operator rank 0 draws it and shares it with the
+ * other ranks through the communicator, so all ranks build the same start vector. */
 SVDLAS2_API int svdlas2_operator_solve(svdlas2_operator *op, uint64_t dimensions, uint64_t iterations,
                            const double end_interval[2], double kappa, uint32_t random_seed,
                            svdlas2_result **out);
@@ -181,7 +183,11 @@ SVDLAS2_API int svdlas2_operator_time_opb(svdlas2_operator *op, int reps, int fl
  * vectors are replicated over the ranks, so on request only rank 0 downloads them and the other ranks return an
  * N-side array of zero columns; the M-side vectors always come out row-sliced per rank); tuning / test overrides
  * of the SpMV: "spmv_variant" (-1 auto, 5 = warp-chunk stream, 0..3 = the tile kernels on the natural CSR arrays),
- * "spmv_hot", "spmv_shape", "spmv_pdl", "spmv_carveout", "spmv_smem_pad_kb" */
+ * "spmv_hot", "spmv_shape", "spmv_pdl", "spmv_carveout", "spmv_smem_pad_kb".  Every knob is stored in the operator it
+ * is set on; nothing is process-wide.
+ * Threading: the library is re-entrant across operators (no global mutable state besides lazily created caches that
+ * are guarded); ONE operator, and ONE communicator, serve one thread at a time (they own a stream, scratch buffers
+ * and collective staging), exactly like a `&mut` borrow in the reference's language. */
 SVDLAS2_API int svdlas2_operator_set(svdlas2_operator *op, const char *knob, int64_t value);
 
 /* ---- multi-GPU, one process per GPU (rows of the oriented operator B sharded by nnz) -- */

@@ -1007,6 +1007,70 @@ void las2_oracle_opb(int fmt, uint64_t nrows, uint64_t ncols, uint64_t nnz, cons
     svd_opa(&A, temp, y, !transposed);
 }
 
+/* Unit costs of the O(N) loops of the path on this host, for bench.py's BOUNDED CPU sample of configs whose full
+ * solve takes hours (time a few svd_opb, one purge pass, imtql2 at the final js, extrapolate with the
+ * counts of the full solve).  The loops are the oracle's own (same helpers, same access pattern: `nvec` stored
+ * vectors of length n streamed once each).  out[0] = seconds per stored vector visited by purge (two ddot + two
+ * daxpy, reference :1374-1382); out[1] = seconds of the BLAS-1 chain of one lanczos_step incl. the storq copy
+ * (:1248-1304); out[2] = seconds per (stored vector, accepted Ritz vector) term of the contraction (:1813-1815). */
+void las2_oracle_unit_costs(uint64_t n, uint64_t nvec, double out[3])
+{
+    if (nvec < 1) nvec = 1;
+    double **q = (double **)malloc(nvec * sizeof(double *));
+    double *w[6];
+    uint64_t state = 0x9E3779B97F4A7C15ull;
+    for (uint64_t v = 0; v < nvec + 6; v++) {
+        double *p = (double *)malloc((n ? n : 1) * sizeof(double));
+        for (uint64_t i = 0; i < n; i++) {
+            state = state * 6364136223846793005ull + 1442695040888963407ull;
+            p[i] = ((double)(state >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 1e-3;
+        }
+        if (v < nvec) q[v] = p; else w[v - nvec] = p;
+    }
+    double *w0 = w[0], *w1 = w[1], *w2 = w[2], *w3 = w[3], *w4 = w[4], *vt = w[5];
+    volatile double sink = 0.0;
+
+    double t0 = now_s();
+    for (uint64_t i = 0; i < nvec; i++) { /* purge, :1374-1382 */
+        double t = svd_ddot(n, q[i], w3);
+        svd_daxpy(n, -t, q[i], w1);
+        t = svd_ddot(n, q[i], w4);
+        svd_daxpy(n, -t, q[i], w0);
+        sink += t;
+    }
+    out[0] = (now_s() - t0) / (double)nvec;
+
+    t0 = now_s();
+    {   /* one lanczos_step without its svd_opb and purge, :1248-1304 */
+        memcpy(q[0], w2, n * sizeof(double)); /* storq */
+        svd_datx(n, 1.0 / 3.0, w0, w1);
+        svd_dscal(n, 1.0 / 3.0, w3);
+        svd_daxpy(n, -1e-3, w2, w0);
+        double a = svd_ddot(n, w0, w3);
+        svd_daxpy(n, -a, w1, w0);
+        double t = svd_ddot(n, w0, w4);
+        svd_daxpy(n, -t, w2, w0);
+        t = svd_ddot(n, w0, w3);
+        svd_daxpy(n, -t, w1, w0);
+        memcpy(w4, w0, n * sizeof(double));
+        sink += svd_norm(n, w4) + a;
+    }
+    out[1] = now_s() - t0;
+
+    t0 = now_s();
+    for (uint64_t i = 0; i < nvec; i++) { /* ritvec contraction, :1813-1815 */
+        const double *qq = q[i];
+        double sv = 1e-3 * (double)(i + 1);
+        for (uint64_t c = 0; c < n; c++) vt[c] += sv * qq[c];
+    }
+    out[2] = (now_s() - t0) / (double)nvec;
+    sink += vt[n ? n - 1 : 0];
+    (void)sink;
+    for (uint64_t v = 0; v < nvec; v++) free(q[v]);
+    for (int k = 0; k < 6; k++) free(w[k]);
+    free(q);
+}
+
 int las2_oracle_imtqlb(uint64_t n, double *d, double *e, double *bnd) { return imtqlb(n, d, e, bnd); }
 int las2_oracle_imtql2(uint64_t nm, uint64_t n, double *d, double *e, double *z) { return imtql2(nm, n, d, e, z); }
 double las2_oracle_pythag(double a, double b) { return svd_pythag(a, b); }

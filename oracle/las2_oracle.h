@@ -66,6 +66,8 @@ void las2_oracle_opa(int fmt, uint64_t nrows, uint64_t ncols, uint64_t nnz, cons
                      const double *values, const double *x, double *y, int transposed);
 void las2_oracle_opb(int fmt, uint64_t nrows, uint64_t ncols, uint64_t nnz, const uint64_t *a, const uint64_t *b,
                      const double *values, const double *x, double *y, double *temp, int transposed);
+/* seconds per purge visit / per lanczos_step BLAS-1 chain / per contraction term on this host (bench.py's bounded sample) */
+void las2_oracle_unit_costs(uint64_t n, uint64_t nvec, double out[3]);
 int las2_oracle_imtqlb(uint64_t n, double *d, double *e, double *bnd);
 int las2_oracle_imtql2(uint64_t nm, uint64_t n, double *d, double *e, double *z);
 double las2_oracle_pythag(double a, double b);

@@ -70,6 +70,8 @@ def lib():
         L.las2_oracle_opb.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p, f64p, f64p, f64p,
                                       f64p, C.c_int]
         L.las2_oracle_opb.restype = None
+        L.las2_oracle_unit_costs.argtypes = [C.c_uint64, C.c_uint64, f64p]
+        L.las2_oracle_unit_costs.restype = None
         L.las2_oracle_imtqlb.argtypes = [C.c_uint64, f64p, f64p, f64p]
         L.las2_oracle_imtqlb.restype = C.c_int
         L.las2_oracle_imtql2.argtypes = [C.c_uint64, C.c_uint64, f64p, f64p, f64p]
@@ -196,6 +198,24 @@ def opb(A, x, transposed=False):
     y = np.zeros(n)
     tmp = np.zeros(m)
     L.las2_oracle_opb(fmt, nr, nc, nnz, _p(a, C.c_uint64), _p(b, C.c_uint64), _p(v, C.c_double),
+                      _p(x, C.c_double), _p(y, C.c_double), _p(tmp, C.c_double), int(transposed))
+    return y
+
+
+def unit_costs(n: int, nvec: int = 8) -> dict:
+    """Seconds per purge visit of a stored vector, per lanczos_step BLAS-1 chain, per Ritz-contraction term (vectors of
+    length n) on this host: the O(N) pieces of bench.py's bounded CPU sample."""
+    out = (C.c_double * 3)()
+    lib().las2_oracle_unit_costs(int(n), int(nvec), out)
+    return dict(purge_vec_s=out[0], step_blas1_s=out[1], contract_term_s=out[2])
+
+
+def opb_raw(fmt: int, nrows: int, ncols: int, a: np.ndarray, b: np.ndarray, v: np.ndarray, x: np.ndarray, transposed: bool):
+    """svd_opb on raw u64 arrays without any conversion copy (the 15 GB of cfg 4)."""
+    L = lib()
+    n, m = (nrows, ncols) if transposed else (ncols, nrows)
+    y, tmp = np.zeros(n), np.zeros(m)
+    L.las2_oracle_opb(fmt, nrows, ncols, len(v), _p(a, C.c_uint64), _p(b, C.c_uint64), _p(v, C.c_double),
                       _p(x, C.c_double), _p(y, C.c_double), _p(tmp, C.c_double), int(transposed))
     return y
 

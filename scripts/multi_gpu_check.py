@@ -15,6 +15,7 @@ ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--scale", type=float, default=0.05)
 ap.add_argument("--dims", type=int, default=30)
 ap.add_argument("--oracle", type=int, default=0)
+ap.add_argument("--seed", type=int, default=12345, help="0: the library draws the seed (rank 0's draw must reach every rank)")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -26,10 +27,11 @@ Bl, lo, hi = sharding.local_shard(B, bounds, rank)
 comm = las2.Communicator(rank, world, sharding.broadcast_comm_id(dist, rank), device=local)
 t0 = time.time()
 with las2.ShardedOperator(Bl, B.shape[0], lo, int(B.nnz), comm, transposed, device=local) as op:
-    r = op.solve(a.dims, random_seed=12345)
+    r = op.solve(a.dims, random_seed=a.seed)
     t_sharded = time.time() - t0
+    seed_used = r.diagnostics.random_seed
     for rep in range(3):
-        rr = op.solve(a.dims, random_seed=12345)
+        rr = op.solve(a.dims, random_seed=seed_used)
         if rank == 0:
             print("PROFILE", rep, json.dumps({k: round(rr.profile[k], 4) for k in ("t_total", "t_lanczos", "t_sync_wait", "t_ritvec", "t_imtql2", "t_download", "t_device")}), flush=True)
         del rr
@@ -46,10 +48,10 @@ mside = r.vt if transposed else r.ut
 parts = [None] * world
 dist.all_gather_object(parts, (lo, mside))
 ok = [None] * world
-dist.all_gather_object(ok, (same_s, same_v, r.diagnostics.lanczos_steps))
+dist.all_gather_object(ok, (same_s, same_v, r.diagnostics.lanczos_steps, seed_used))
 if rank == 0:
     M_full = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])], axis=1)
-    single = las2.svd_dim_seed(A, a.dims, 12345)
+    single = las2.svd_dim_seed(A, a.dims, seed_used)
     s_m = single.vt if transposed else single.ut
     s_n = single.ut if transposed else single.vt
     out = dict(world=world, workload=a.workload, shape=list(A.shape), nnz=int(A.nnz), transposed=transposed,
@@ -60,10 +62,10 @@ if rank == 0:
                max_rel_dsigma=float(np.max(np.abs(r.s - single.s) / single.s)) if r.d == single.d else None,
                min_cos_n=float(min(abs(nside[i] @ s_n[i]) for i in range(min(r.d, single.d)))),
                min_cos_m=float(min(abs(M_full[i] @ s_m[i]) for i in range(min(r.d, single.d)))),
-               t_sharded=t_sharded, ms_per_opb=tm["ms_per_opb"])
+               t_sharded=t_sharded, ms_per_opb=tm["ms_per_opb"], seed_requested=a.seed, seeds_used=[int(o[3]) for o in ok])
     if a.oracle:
         from oracle import oracle as O
-        o = O.svd_dim_seed(A, a.dims, 12345)
+        o = O.svd_dim_seed(A, a.dims, seed_used)
         out.update(steps_oracle=o.diagnostics["lanczos_steps"], accepted_oracle=o.diagnostics["singular_values"],
                    max_rel_dsigma_vs_oracle=float(np.max(np.abs(r.s - o.s) / o.s)) if o.d == r.d else None)
     print("MULTI " + json.dumps(out), flush=True)

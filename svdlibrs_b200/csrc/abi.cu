@@ -304,12 +304,14 @@ int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value)
     if (!op || !knob) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
     if (!std::strcmp(knob, "profile")) { op->profile = value != 0; return SVDLAS2_OK; }
     if (!std::strcmp(knob, "nside_on_rank0_only")) { op->nside_on_rank0_only = value != 0; return SVDLAS2_OK; }
-    if (!std::strcmp(knob, "spmv_variant")) { g_spmv_variant = (int)value; return SVDLAS2_OK; }
-    if (!std::strcmp(knob, "spmv_hot")) { g_spmv_hot_entries = (int)value; return SVDLAS2_OK; }
-    if (!std::strcmp(knob, "spmv_smem_pad_kb")) { g_chunk_smem_pad_kb = (int)value; return SVDLAS2_OK; }
-    if (!std::strcmp(knob, "spmv_pdl")) { g_chunk_pdl = (int)value; return SVDLAS2_OK; }
-    if (!std::strcmp(knob, "spmv_shape")) { g_chunk_shape = (int)value; return SVDLAS2_OK; }
-    if (!std::strcmp(knob, "spmv_carveout")) { g_chunk_carveout_pct = (int)value; return SVDLAS2_OK; }
+    // SpMV tuning: stored in THIS operator's two matrices (no process-wide state)
+    auto both = [&](int SpmvTuning::*field) { op->B.tune.*field = (int)value; op->BT.tune.*field = (int)value; return SVDLAS2_OK; };
+    if (!std::strcmp(knob, "spmv_variant")) return both(&SpmvTuning::variant);
+    if (!std::strcmp(knob, "spmv_hot")) return both(&SpmvTuning::hot_entries);
+    if (!std::strcmp(knob, "spmv_smem_pad_kb")) return both(&SpmvTuning::smem_pad_kb);
+    if (!std::strcmp(knob, "spmv_pdl")) return both(&SpmvTuning::pdl);
+    if (!std::strcmp(knob, "spmv_shape")) return both(&SpmvTuning::shape);
+    if (!std::strcmp(knob, "spmv_carveout")) return both(&SpmvTuning::carveout_pct);
     return fail(SVDLAS2_ERR_INVALID_ARGUMENT, std::string("unknown knob ") + knob);
 }
 

@@ -512,27 +512,22 @@ int g_chunk_carve[kMaxDevicesTracked][6]; // carve-out (+1) currently set on eac
 
 } // namespace
 
-int g_chunk_smem_pad_kb = 0;  // tuning knob "spmv_smem_pad_kb": extra (unused) dynamic shared memory
-int g_chunk_pdl = -1;          // tuning knob "spmv_pdl": programmatic dependent launch of the SpMV kernel chain (-1: SVDLAS2_PDL, default on)
-int g_chunk_shape = 32;        // tuning knob "spmv_shape": 32 = 32 warps x 1 stage, 16 = 16 warps x 2 stages
-int g_chunk_carveout_pct = -1; // tuning knob "spmv_carveout": shared-memory carve-out in percent of 228 KB (-1: exact fit)
-
 
 
 namespace {
 
 // Programmatic dependent launch of the SpMV kernel chain (~2 % per opb at cfg 2; Nsight Compute lists and times the
 // kernels either way).  Knob "spmv_pdl" or SVDLAS2_PDL=0 turns it off.
-bool chunk_pdl_enabled() {
+bool chunk_pdl_enabled(int knob) {
     static const int env = [] { const char *e = std::getenv("SVDLAS2_PDL"); return e ? std::atoi(e) : -1; }();
-    return g_chunk_pdl >= 0 ? g_chunk_pdl != 0 : env != 0;
+    return knob >= 0 ? knob != 0 : env != 0;
 }
 
 // Launch with programmatic stream serialisation: the kernel may start while its predecessor in the stream drains; it
 // must call cudaGridDependencySynchronize() before touching anything the predecessor wrote (or still reads).
 template <typename... KArgs, typename... Args>
-void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
-    if (!chunk_pdl_enabled()) { // the plain launch path: visible to every profiler
+void launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    if (!pdl) { // the plain launch path: visible to every profiler
         kernel<<<grid, block, smem, s>>>(static_cast<KArgs>(args)...);
         return;
     }
@@ -718,16 +713,16 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
     if (K.slabs) {
         hot = kSlabWidth;
     } else {
-        hot = g_spmv_hot_entries >= 0 ? (u32)g_spmv_hot_entries : std::min<u32>(A.hot_entries, kChunkHotDefault);
+        hot = A.tune.hot_entries >= 0 ? (u32)A.tune.hot_entries : std::min<u32>(A.hot_entries, kChunkHotDefault);
         hot = std::min<u32>(hot, kChunkHotMax);
         hot = (u32)std::min<u64>(hot, K.cols);
     }
-    const size_t smem = std::min<size_t>(chunk_smem_bytes(hot) + (size_t)g_chunk_smem_pad_kb * 1024, 227 * 1024);
+    const size_t smem = std::min<size_t>(chunk_smem_bytes(hot) + (size_t)A.tune.smem_pad_kb * 1024, 227 * 1024);
     // The shared-memory carve-out is set explicitly to what this launch needs: left to itself the driver picks the
     // carve-out that would fit the most CTAs per SM (e.g. 196 KB for a 98 KB kernel), and the gathers then lose the
     // L1 lines their misses land in (scripts/micro/gather_l1_sweep.cu: 0.95 gathers/clk/SM with <= 132 KB carved
     // out, 0.43 with 228 KB).
-    const int carve = g_chunk_carveout_pct >= 0 ? g_chunk_carveout_pct : (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1);
+    const int carve = A.tune.carveout_pct >= 0 ? A.tune.carveout_pct : (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1);
     const int dev_slot = current_device_slot();
     auto configure = [&](const void *fn, int &cached) {
         if (cached == carve + 1) return;
@@ -736,7 +731,8 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
         cached = carve + 1;
     };
     // launch shape: 32 warps x 1 stage unless the knob "spmv_shape" says 16 x 2 (value 16)
-    const bool wide = g_chunk_shape != 16;
+    const bool wide = A.tune.shape != 16;
+    const bool pdl = chunk_pdl_enabled(A.tune.pdl);
     const u32 warps = wide ? 32 : 16;
     const u32 grid = std::min<u32>(kNumSMs, cdiv(K.num_chunks, warps));
     const u32 *rowmap = (!K.slabs && K.has_empty_rows) ? K.rowmap.get() : nullptr;
@@ -746,7 +742,7 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
 #define LAS2_CHUNK_LAUNCH(MODE, WARPS, STAGES, SLOT)                                                                   \
     do {                                                                                                               \
         configure((const void *)k_spmv_chunk<MODE, WARPS, STAGES>, g_chunk_carve[dev_slot][SLOT]);                               \
-        launch_pdl(k_spmv_chunk<MODE, WARPS, STAGES>, dim3(grid), dim3(WARPS * 32), smem, s, (const uint4 *)K.data,       \
+        launch_pdl(pdl, k_spmv_chunk<MODE, WARPS, STAGES>, dim3(grid), dim3(WARPS * 32), smem, s, (const uint4 *)K.data,       \
                    (const u32 *)K.chunk_row, rowmap, x, out, (double *)K.carry, (double *)K.head, K.num_chunks,          \
                    mode == 2 ? 0u : hot, (const u32 *)K.slab_chunk_start, K.nslabs, (u32)K.cols);                      \
     } while (0)
@@ -754,11 +750,11 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
     else if (mode == 1) { if (wide) LAS2_CHUNK_LAUNCH(1, 32, 1, 2); else LAS2_CHUNK_LAUNCH(1, 16, 2, 3); }
     else { if (wide) LAS2_CHUNK_LAUNCH(0, 32, 1, 4); else LAS2_CHUNK_LAUNCH(0, 16, 2, 5); }
 #undef LAS2_CHUNK_LAUNCH
-    launch_pdl(k_chunk_fixup, dim3(cdiv(K.num_chunks, 256)), dim3(256), 0, s, (const u32 *)K.fix_row, (const u32 *)K.fix_first,
+    launch_pdl(pdl, k_chunk_fixup, dim3(cdiv(K.num_chunks, 256)), dim3(256), 0, s, (const u32 *)K.fix_row, (const u32 *)K.fix_first,
                (const double *)K.carry, (const double *)K.head, out, K.num_chunks);
     if (launches) *launches += 2;
     if (mode == 2) {
-        launch_pdl(k_slab_reduce, dim3(cdiv(K.rows, 32)), dim3(kReduceWarps * 32), 0, s, (const u32 *)K.piece_id,
+        launch_pdl(pdl, k_slab_reduce, dim3(cdiv(K.rows, 32)), dim3(kReduceWarps * 32), 0, s, (const u32 *)K.piece_id,
                    (const double *)K.part, (u64)K.rows, K.nslabs, y);
         if (launches) *launches += 1;
     }

@@ -52,8 +52,20 @@ struct ChunkStream {
     u64 stream_bytes = 0;           // bytes one SpMV moves with this format (reporting)
 };
 
+// Per-matrix SpMV tuning knobs (svdlas2_operator_set "spmv_*"): they belong to the operator they were set on, so two
+// operators of one process never see each other's settings (the driver is re-entrant).
+struct SpmvTuning {
+    int variant = -1;      // -1 auto; 0/1/2 tile kernels with 256/128/512 threads, 3 persistent hot-prefix tile kernel, 5 chunk stream
+    int hot_entries = -1;  // -1 auto; entries of the gathered vector kept in shared memory
+    int carveout_pct = -1; // chunk kernel: shared-memory carve-out in percent of 228 KB (-1: exact fit)
+    int pdl = -1;          // chunk kernel chain: programmatic dependent launch (-1: SVDLAS2_PDL, default on)
+    int shape = 32;        // chunk kernel: 32 warps x 1 stage, or 16 warps x 2 stages (value 16)
+    int smem_pad_kb = 0;   // chunk kernel: extra (unused) dynamic shared memory
+};
+
 struct DeviceCsr {
     u64 rows = 0, cols = 0, nnz = 0;
+    SpmvTuning tune;
     ChunkStream chk;
     DevBuf<u32> off;    // rows + 1 row offsets
     DevBuf<u32> idx;    // padded_nnz column indices (padding: index 0)

@@ -164,7 +164,8 @@ struct Solver {
         double rnm2;
         gather({0}, &rnm2);
         // the reference retries up to three times with the SAME regenerated vector, so one try decides
-        if (!(rnm2 > 0.0)) throw Error(SVDLAS2_ERR_STARTV, "rnm2 <= 0.0, rnm2 = " + std::to_string(rnm2));
+        // (a NaN passes this test exactly as in the reference, :1127, and surfaces later as ImtqlbError)
+        if (rnm2 <= 0.0) throw Error(SVDLAS2_ERR_STARTV, "rnm2 <= 0.0, rnm2 = " + std::to_string(rnm2));
         if (step > 0) {
             // w0 -= (w3 . q_i) q_i with w3 the frozen copy: classical GS against all stored vectors, :1132-1135
             panel_cgs2(Q.get(), ld, N, 0, (u32)step, r.get(), nullptr, pw, &slot[1], &slot[2], nullptr, s,
@@ -547,7 +548,21 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
            uint32_t random_seed, svdlas2_result *res) {
     const double t0 = wall();
     LAS2_CUDA(cudaSetDevice(op.device));
-    if (!(random_seed > 0)) random_seed = entropy_seed_u32(); // :578-581
+    if (!(random_seed > 0)) {
+        random_seed = entropy_seed_u32(); // :578-581
+        if (op.comm) {
+            // every rank must build the SAME start vector: rank 0's draw wins (a sum in which the other ranks add zero;
+            // a u32 is exact in a double)
+            DevBuf<double> sd(1);
+            const double mine = op.comm->rank() == 0 ? (double)random_seed : 0.0;
+            LAS2_CUDA(cudaMemcpyAsync(sd.get(), &mine, sizeof(double), cudaMemcpyHostToDevice, op.stream));
+            op.comm->allreduce_sum(sd.get(), 1, op.stream);
+            double got = 0.0;
+            LAS2_CUDA(cudaMemcpyAsync(&got, sd.get(), sizeof(double), cudaMemcpyDeviceToHost, op.stream));
+            LAS2_CUDA(cudaStreamSynchronize(op.stream));
+            random_seed = (uint32_t)got;
+        }
+    }
 
     // clamping uses the un-oriented shape (:583-594)
     const u64 mn = std::min(op.a_rows, op.a_cols);

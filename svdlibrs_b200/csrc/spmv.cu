@@ -258,8 +258,6 @@ __global__ void k_spmv_fixup(const u32 *__restrict__ fix_row, const u32 *__restr
 
 } // namespace
 
-int g_spmv_variant = -1;
-int g_spmv_hot_entries = -1; // -1 auto
 
 namespace {
 constexpr u32 kHotMaxEntries = 16384; // upper bound of the knob: 128 KB of the 227 KB
@@ -271,16 +269,16 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
 
 void spmv(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
     if (A.rows == 0) return;
-    if (A.chk.active && (g_spmv_variant < 0 || g_spmv_variant == 5)) {
+    if (A.chk.active && (A.tune.variant < 0 || A.tune.variant == 5)) {
         spmv_chunk(A, x, y, s, launches);
         return;
     }
     // variant: -1 auto, 0/1/2 = one CTA per tile with 256/128/512 threads, 3 = persistent hot-prefix kernel
-    int variant = g_spmv_variant;
+    int variant = A.tune.variant;
     if (variant < 0) variant = (A.num_tiles >= 8u * kNumSMs) ? 3 : 0;
     switch (variant) {
     case 3: {
-        u32 hot = g_spmv_hot_entries >= 0 ? (u32)g_spmv_hot_entries : A.hot_entries;
+        u32 hot = A.tune.hot_entries >= 0 ? (u32)A.tune.hot_entries : A.hot_entries;
         if (hot > kHotMaxEntries) hot = kHotMaxEntries;
         if (hot > A.cols) hot = (u32)A.cols;
         bool &attr_set = g_hot_attr_set[current_device_slot()];

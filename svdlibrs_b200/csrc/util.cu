@@ -12,6 +12,7 @@ constexpr int kMaxDevices = 64;
 struct PoolState {
     std::mutex mu;
     cudaStream_t stream[kMaxDevices] = {};
+    cudaMemPool_t pool[kMaxDevices] = {};
     bool ready[kMaxDevices] = {};
     bool legacy = false; // SVDLAS2_DEVICE_POOL=0: plain cudaMalloc / cudaFree
 };
@@ -32,10 +33,16 @@ cudaStream_t alloc_stream(int dev) {
     std::lock_guard<std::mutex> lk(S.mu);
     if (!S.ready[dev]) {
         LAS2_CUDA(cudaStreamCreateWithFlags(&S.stream[dev], cudaStreamNonBlocking));
-        cudaMemPool_t pool;
-        LAS2_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        // a PRIVATE pool: the release threshold is lifted on it, not on the device's default pool that the host
+        // application's own cudaMallocAsync calls use
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        LAS2_CUDA(cudaMemPoolCreate(&S.pool[dev], &props));
         uint64_t keep = UINT64_MAX;
-        LAS2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        LAS2_CUDA(cudaMemPoolSetAttribute(S.pool[dev], cudaMemPoolAttrReleaseThreshold, &keep));
         S.ready[dev] = true;
     }
     return S.stream[dev];
@@ -53,7 +60,7 @@ void *device_alloc(size_t bytes) {
         e = cudaMalloc(&p, bytes);
     } else {
         cudaStream_t as = alloc_stream(dev);
-        e = cudaMallocAsync(&p, bytes, as);
+        e = cudaMallocFromPoolAsync(&p, bytes, state().pool[dev], as);
         if (e == cudaSuccess) e = cudaStreamSynchronize(as);
     }
     if (e != cudaSuccess) {
@@ -78,8 +85,7 @@ void device_pool_trim() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return;
     cudaDeviceSynchronize();
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    if (dev < kMaxDevices && state().ready[dev]) cudaMemPoolTrimTo(state().pool[dev], 0);
 }
 
 } // namespace las2

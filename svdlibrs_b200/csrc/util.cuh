@@ -37,7 +37,7 @@ struct Error : std::runtime_error {
 
 #define LAS2_LAUNCH_CHECK() LAS2_CUDA(cudaGetLastError())
 
-// Device memory comes from the device's stream-ordered pool with the release threshold lifted, so that the buffers a
+// Device memory comes from a private stream-ordered pool (one per device) with the release threshold lifted, so that the buffers a
 // solve frees (Lanczos panel, U/V, upload scratch) are handed back to the next allocation in microseconds instead
 // of being unmapped and mapped again by cudaFree / cudaMalloc (tens of milliseconds of jitter per solve on B200).
 // device_alloc returns memory that is immediately usable on any stream; device_free waits for the device like

@@ -59,3 +59,21 @@ def test_sharded_solve_matches_single_gpu_and_oracle(workload, scale, dims, shar
     assert r["d_sharded"] == r["d_single"]
     assert r["max_rel_dsigma"] <= 1e-10 and r["max_rel_dsigma_vs_oracle"] <= 1e-10
     assert r["min_cos_n"] >= 1 - 1e-8 and r["min_cos_m"] >= 1 - 1e-8
+
+
+def test_seed_zero_is_shared_by_all_ranks():
+    """random_seed == 0 ("draw one", reference src/lib.rs:578-581): rank 0's draw must reach every rank, otherwise the ranks
+    build different start vectors and the replicated state diverges (silently wrong sums, mismatched collectives)."""
+    if n_gpus() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = min(n_gpus(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py"),
+           "--workload", "cfg2", "--scale", "0.03", "--dims", "20", "--oracle", "1", "--seed", "0"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    r = json.loads([l for l in p.stdout.splitlines() if l.startswith("MULTI ")][-1][len("MULTI "):])
+    assert len(set(r["seeds_used"])) == 1 and r["seeds_used"][0] > 0
+    assert r["all_ranks_identical"]
+    assert r["steps_sharded"] == r["steps_single"] == r["steps_oracle"]
+    assert r["max_rel_dsigma"] <= 1e-10 and r["max_rel_dsigma_vs_oracle"] <= 1e-10

@@ -86,6 +86,35 @@ def test_errors_match_reference(las2):
     assert e.value.kind == "StartvError"
 
 
+def test_error_codes_1_3_4_match_the_oracle(las2, oracle):
+    """The remaining SvdLibError variants (src/error.rs:8-26): the same inputs fail the same way in both implementations.
+    ImtqlbError (:1016): a NaN entry survives startv (`rnm2 <= 0.0` is false for NaN, :1127) and stops the first analysis of T
+    after 30 QL iterations; StponeError (:1183): entries so small that |B'B x| < eps; Imtql2Error (:1612) cannot be reached
+    through the driver with finite data, so the QL routine is driven directly through the test hook."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    A = sp.random(60, 40, density=0.2, format="csr", random_state=1)
+    bad = A.copy(); bad.data[3] = np.nan
+    for M, kind, code in ((bad, "ImtqlbError", 1), ((A * 1e-10).tocsr(), "StponeError", 3)):
+        with pytest.raises(oracle.OracleError) as eo:
+            oracle.svd_dim_seed(M, 5, 12345)
+        with pytest.raises(las2.SvdLibError) as eg:
+            las2.svd_dim_seed(M, 5, 12345)
+        assert eo.value.code == code and eg.value.code == code and eg.value.kind == kind
+        assert eg.value.message == eo.value.message
+    assert las2.svd_dim_seed(A, 5, 12345).d == 5  # the library is still usable afterwards
+    from svdlibrs_b200 import _lib
+    L = _lib.lib()
+    f64p = C.POINTER(C.c_double)
+    L.svdlas2_test_ql_vectors.argtypes = [C.c_uint64, f64p, f64p, f64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.svdlas2_test_ql_vectors.restype = C.c_int
+    d, e, z = np.array([1.0, np.nan, 2.0]), np.array([0.0, 0.5, 0.5]), np.zeros(9)
+    rc_o, _, _ = oracle.imtql2(d, e)
+    rc_g = L.svdlas2_test_ql_vectors(3, d.ctypes.data_as(f64p), e.ctypes.data_as(f64p), z.ctypes.data_as(f64p), None, None)
+    assert rc_o == 4 and rc_g == 4
+    del rng
+
+
 def test_malformed_arrays_are_rejected(las2):
     A = sp.csr_matrix(GOLDEN_M)
     bad = sp.csr_matrix(GOLDEN_M)
@@ -306,8 +335,9 @@ def test_every_spmv_variant_matches_oracle(las2, oracle, variant, hot):
                 os.environ.pop("SVDLAS2_SLABS", None)
 
 
-def test_cfg2_full_size_invariants(las2):
-    """BASELINE configs[1] at FULL size (1M x 100k, ~4.5e7 nnz, dims 100) through size-independent properties:
+def test_cfg2_full_size_parity_and_invariants(las2, oracle):
+    """BASELINE configs[1] at FULL size (1M x 100k, ~4.5e7 nnz, dims 100): the whole solve against the oracle on the same
+    matrix and seed (north-star tolerances; the oracle needs about a minute on one core), and size-independent properties:
     every SpMV kernel agrees with the parity-tested one on the same vector (catches races that only show under
     load), singular values descend, V rows are orthonormal, A v = sigma u and A' u = sigma v hold per triplet."""
     from svdlibrs_b200 import synthetic
@@ -327,6 +357,7 @@ def test_cfg2_full_size_invariants(las2):
         r = op.solve(dims, random_seed=12345)
         r2 = op.solve(dims, random_seed=12345)
     assert r == r2                                     # deterministic
+    assert_svd_parity(r, oracle.svd_dim_seed(A, dims, 12345))
     assert r.d == dims and np.all(np.diff(r.s) <= 0)
     assert orthonormality_defect(r.vt) < 1e-8
     for i in (0, 1, dims // 2, dims - 1):
@@ -336,9 +367,10 @@ def test_cfg2_full_size_invariants(las2):
         assert np.linalg.norm(atu - r.s[i] * r.vt[i]) <= 1e-6 * r.s[0]   # Ritz residual: bounded by kappa-level accuracy
 
 
-def test_cfg3_full_size_invariants(las2):
+def test_cfg3_full_size_parity_and_invariants(las2, oracle):
     """BASELINE configs[2] at FULL size (wide CSC 200k x 2M, ~9.1e7 nnz, dims 100: the internal-transpose path, slab mode
-    on the B' side) through size-independent properties: chunk-stream kernels agree with the tile kernel on the same
+    on the B' side): the whole solve against the oracle on the same matrix and seed (north-star tolerances; about two
+    minutes of one core), and size-independent properties: chunk-stream kernels agree with the tile kernel on the same
     vector, repeat solves are bit-identical, ut / vt come back un-swapped with the right shapes, sigma descends, the
     N-side vectors are orthonormal, A v = sigma u per triplet."""
     from svdlibrs_b200 import synthetic
@@ -357,8 +389,30 @@ def test_cfg3_full_size_invariants(las2):
         r = op.solve(dims, random_seed=12345)
         r2 = op.solve(dims, random_seed=12345)
     assert r == r2
+    assert_svd_parity(r, oracle.svd_dim_seed(A, dims, 12345))
     assert r.diagnostics.transposed and r.ut.shape == (dims, A.shape[0]) and r.vt.shape == (dims, A.shape[1])
     assert r.d == dims and np.all(np.diff(r.s) <= 0)
     assert orthonormality_defect(r.ut) < 1e-8  # rows(A) = 200k is the N side of the transposed operator
     for i in (0, dims // 2, dims - 1):
         assert np.linalg.norm(A.T @ r.ut[i] - r.s[i] * r.vt[i]) <= 1e-9 * r.s[0]
+
+
+@pytest.mark.parametrize("name", ["cfg4", "cfg5"])
+def test_full_size_against_the_recorded_oracle_run(name):
+    """BASELINE configs[3] (1e9 nnz, dims 200: the north-star configuration) and configs[4] (dims 1000, 2252 Lanczos steps) at
+    FULL size against the CPU oracle's own full-size run of the same matrix and seed, recorded once on the build box
+    (hours of one core; tests/golden/oracle_<cfg>.json by scripts/make_oracle_fixtures.py): identical counts, sigma to 1e-10,
+    the recorded sketch of U and V inside the bound that |cos| >= 1 - 1e-8 implies, and the invariants of the result."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "tests", "golden", f"oracle_{name}.json")):
+        pytest.skip("fixture not recorded yet")
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "fixture_check.py"), name], capture_output=True, text=True,
+                       timeout=1500, cwd=root)
+    assert p.returncode == 0, p.stderr[-3000:]
+    r = json.loads([l for l in p.stdout.splitlines() if l.startswith("FIXTURE ")][-1][len("FIXTURE "):])
+    assert r["counts_equal"], r
+    assert r["max_rel_dsigma"] is not None and r["max_rel_dsigma"] <= 1e-10, r
+    assert r["alf_head_rel"] <= 1e-9, r
+    assert all(v <= r["sketch_bound"] for v in r["sketch_worst"].values()), r
+    assert r["sigma_descending"] and r["vt_gram_defect"] < 1e-8 and r["resid_av"] <= 1e-9 and r["resid_atu"] <= 1e-6, r

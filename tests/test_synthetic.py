@@ -27,3 +27,21 @@ def test_configs_are_deterministic_and_shaped():
     assert C3.format == "csc" and C3.shape[1] >= 1.2 * C3.shape[0]
     A1, d1 = synthetic.make("cfg1", scale=0.1)
     assert A1.format == "csr" and d1 == 20 and A1.has_sorted_indices
+
+
+def test_parallel_generation_is_bit_identical():
+    """bench.py fans the independent 200k-row chunks over forked workers (cfg 4 is 9.2e8 non-zeros): same bits for any
+    worker count and any row range."""
+    kw = dict(nrows=60_000, ncols=4_000, nnz=900_000, seed=12345, chunk_rows=7_000)
+    a = synthetic.powerlaw_arrays(**kw, workers=1)
+    b = synthetic.powerlaw_arrays(**kw, workers=4)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    lo, hi = 12_345, 43_210
+    c = synthetic.powerlaw_arrays(**kw, workers=3, rows=(lo, hi))
+    assert np.array_equal(c[0], a[0][lo:hi + 1] - a[0][lo])
+    assert np.array_equal(c[1], a[1][a[0][lo]:a[0][hi]]) and np.array_equal(c[2], a[2][a[0][lo]:a[0][hi]])
+
+
+def test_oracle_unit_costs_are_positive(oracle):
+    u = oracle.unit_costs(50_000, 4)
+    assert all(v > 0 for v in u.values())
