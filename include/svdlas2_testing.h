@@ -33,6 +33,11 @@ SVDLAS2_API void svdlas2_test_cosort(uint64_t n, double *keys, double *vals);
 SVDLAS2_API int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, int device, double *ms_dots,
                                         double *ms_update);
 
+/* GPU test hook for the 4-right-hand-side product of the ritvec tail (k_spmm4_chunk): Y[r] = B X[r] for r < nv <= 4 on the
+ * oriented operator of `op`; X holds nv vectors of N doubles, Y receives nv vectors of M doubles, sumsq[r] = |Y[r]|^2 as the
+ * tail computes it.  Returns SVDLAS2_ERR_INVALID_ARGUMENT when the operator's B is not on the chunk stream. */
+SVDLAS2_API int svdlas2_test_spmm4(svdlas2_operator *op, uint32_t nv, const double *X, double *Y, double *sumsq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,6 +299,30 @@ int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, int device, do
     });
 }
 
+int svdlas2_test_spmm4(svdlas2_operator *op_, uint32_t nv, const double *X, double *Y, double *sumsq) {
+    Operator *op = reinterpret_cast<Operator *>(op_);
+    if (!op || !X || !Y || nv < 1 || nv > 4) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        LAS2_CUDA(cudaSetDevice(op->device));
+        if (!spmm4_supported(op->B)) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "B is not on the (plain) chunk stream");
+        cudaStream_t s = op->stream;
+        const u64 N = op->N, M = op->M, ld = (N + 31) / 32 * 32;
+        DevBuf<double> dx((size_t)nv * ld), dy((size_t)nv * M), ds(nv);
+        LAS2_CUDA(cudaMemsetAsync(dx.get(), 0, (size_t)nv * ld * sizeof(double), s));
+        LAS2_CUDA(cudaMemcpy2DAsync(dx.get(), ld * sizeof(double), X, N * sizeof(double), N * sizeof(double), nv, cudaMemcpyHostToDevice, s));
+        LAS2_CUDA(cudaMemsetAsync(dy.get(), 0xff, (size_t)nv * M * sizeof(double), s));
+        Spmm4Work w4;
+        const int np = spmm4(op->B, dx.get(), ld, nv, dy.get(), M, w4, s);
+        GatherList g;
+        g.count = (int)nv;
+        for (uint32_t r = 0; r < nv; r++) { g.parts[r] = w4.parts.get() + (size_t)r * kMaxParts; g.nparts[r] = np; }
+        gather_scalars(g, ds.get(), s);
+        LAS2_CUDA(cudaMemcpyAsync(Y, dy.get(), (size_t)nv * M * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (sumsq) LAS2_CUDA(cudaMemcpyAsync(sumsq, ds.get(), nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        LAS2_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value) {
     Operator *op = reinterpret_cast<Operator *>(op_);
     if (!op || !knob) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");

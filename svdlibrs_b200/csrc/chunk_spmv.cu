@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "spmv.cuh"
+#include "vecops.cuh"
 
 namespace las2 {
 
@@ -508,6 +509,251 @@ k_chunk_fixup(const u32 *__restrict__ fix_row, const u32 *__restrict__ fix_first
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 4 right-hand sides
+// Y4 = A X4 for FOUR vectors at once (the sigma / U tail of ritvec, reference src/lib.rs:1839-1859, applies the operator to
+// every accepted Ritz vector: d SpMVs that re-read the matrix d times).  X4 is row-interleaved (cols x 4 doubles), so the
+// gather of one non-zero is ONE 32-byte sector that serves four vectors -- the L1TEX tag stage, which bounds the SpMV at
+// ~1 gather per clock per SM, is paid once per four results -- and the 12 B/nnz stream is read once per four vectors.
+// Same chunk stream, same per-lane order of the multiply-adds and the same segmented scan as k_spmv_chunk, applied to each
+// of the four columns: every column of Y4 is bit-identical to the SpMV of that column.  16 warps x 2 stages (the 4-wide
+// accumulators and gathers need ~120 registers per thread).
+struct D4 { double v[4]; };
+__device__ __forceinline__ D4 ld_gather4(const double *p, u64 pol) {
+    D4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_row4(double *p, const D4 &a) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.v[0]), "d"(a.v[1]), "d"(a.v[2]), "d"(a.v[3]) : "memory");
+}
+
+template <int STAGES>
+__device__ __forceinline__ void chunk_walk4(u32 first, u32 stop, u32 step, int lane, unsigned long long *bar,
+                                            unsigned char *stage, u32 &phases, const uint4 *__restrict__ data,
+                                            const u32 *__restrict__ chunk_row, const u32 *__restrict__ rowmap,
+                                            const double *__restrict__ x4, double *__restrict__ y4,
+                                            double *__restrict__ carry4, double *__restrict__ head4, u64 pol_stream, u64 pol_keep) {
+    if (first >= stop) return;
+    u32 c = first;
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < STAGES; j++) {
+            if (c + j * step < stop) {
+                mbar_expect_tx(&bar[j], kChunkBytes);
+                bulk_load(stage + j * kChunkBytes, data + (u64)(c + j * step) * (kChunkBytes / 16), kChunkBytes, &bar[j], pol_stream);
+            }
+        }
+    }
+    const u32 lt_mask = (1u << lane) - 1u;
+    u32 cr_next = chunk_row[c];
+    for (u32 it = 0; c < stop; c += step, it++) {
+        const u32 sidx = STAGES == 1 ? 0u : (it & 1u);
+        const u32 cr = cr_next;
+        if (c + step < stop) cr_next = chunk_row[c + step];
+        mbar_wait(&bar[sidx], (phases >> sidx) & 1u);
+        phases ^= 1u << sidx;
+        const uint4 *st = reinterpret_cast<const uint4 *>(stage + sidx * kChunkBytes);
+        uint4 q[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) q[j] = st[j * 32 + lane];
+        double v[kChunkE];
+        u32 ci[kChunkE];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { v[2 * j] = u2d(q[j].x, q[j].y); v[2 * j + 1] = u2d(q[j].z, q[j].w); }
+        ci[0] = q[4].x; ci[1] = q[4].y; ci[2] = q[4].z; ci[3] = q[4].w;
+        ci[4] = q[5].x; ci[5] = q[5].y; ci[6] = q[5].z; ci[7] = q[5].w;
+
+        const u32 c0 = cr & ~kChunkFlag;
+        D4 hsum = {{0.0, 0.0, 0.0, 0.0}}, tsum = {{0.0, 0.0, 0.0, 0.0}};
+        bool seen = false;
+        u32 base = 0;
+        const bool slow = (cr & kChunkFlag) != 0;
+        if (slow) {
+            u32 nf = 0;
+#pragma unroll
+            for (int k = 0; k < (int)kChunkE; k++) nf += ci[k] >> 31;
+#pragma unroll
+            for (int b = 0; b < 4; b++) base += (u32)__popc(__ballot_sync(0xffffffffu, (nf >> b) & 1u) & lt_mask) << b;
+        }
+        u32 j = 0;
+        // two halves of four elements: 4 x 32-byte gathers in flight per lane
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            D4 xv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) xv[k] = ld_gather4(x4 + (u64)(ci[4 * h + k] & ~kChunkFlag) * 4, pol_keep);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int e = 4 * h + k;
+                if ((int)ci[e] < 0) {
+                    if (slow) {
+                        if (seen) { // the row opened by this lane's previous start is complete
+                            const u32 cr_ = c0 + base + j - 1;
+                            st_row4(y4 + (u64)(rowmap ? rowmap[cr_] : cr_) * 4, tsum);
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; r++) tsum.v[r] = 0.0;
+                        j++;
+                    }
+                    seen = true;
+                }
+                if (seen) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) tsum.v[r] = fma(v[e], xv[k].v[r], tsum.v[r]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) hsum.v[r] = fma(v[e], xv[k].v[r], hsum.v[r]);
+                }
+            }
+        }
+        if (slow) __syncwarp();
+
+        const u32 mask = __ballot_sync(0xffffffffu, seen);
+        if (lane == 0 && c + STAGES * step < stop) {
+            mbar_expect_tx(&bar[sidx], kChunkBytes);
+            bulk_load(stage + sidx * kChunkBytes, data + (u64)(c + STAGES * step) * (kChunkBytes / 16), kChunkBytes, &bar[sidx],
+                      pol_stream);
+        }
+        if (!slow) base = __popc(mask & lt_mask);
+        D4 xsum;
+#pragma unroll
+        for (int r = 0; r < 4; r++) xsum.v[r] = seen ? tsum.v[r] : hsum.v[r];
+        const u32 le = mask & (lt_mask | (1u << lane));
+        const int dist = le ? (lane - (31 - __clz(le))) : lane;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const double up = __shfl_up_sync(0xffffffffu, xsum.v[r], o);
+                if (dist >= o) xsum.v[r] += up;
+            }
+        }
+        D4 cin;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            cin.v[r] = __shfl_up_sync(0xffffffffu, xsum.v[r], 1);
+            if (lane == 0) cin.v[r] = 0.0;
+        }
+        if (seen) {
+            D4 total;
+#pragma unroll
+            for (int r = 0; r < 4; r++) total.v[r] = cin.v[r] + hsum.v[r];
+            if ((mask & lt_mask) == 0) {
+                st_row4(head4 + (u64)c * 4, total);
+            } else {
+                const u32 cr_ = c0 + base - 1;
+                st_row4(y4 + (u64)(rowmap ? rowmap[cr_] : cr_) * 4, total);
+            }
+        }
+        if (lane == 31) st_row4(carry4 + (u64)c * 4, xsum);
+    }
+}
+
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_spmm4_chunk(const uint4 *__restrict__ data, const u32 *__restrict__ chunk_row, const u32 *__restrict__ rowmap,
+              const double *__restrict__ x4, double *__restrict__ y4, double *__restrict__ carry4,
+              double *__restrict__ head4, u32 num_chunks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned char *stages = smem_raw + kChunkBarBytes;
+    static_assert(WARPS * STAGES * kChunkBytes == kChunkStageBytesTotal, "stages fill 96 KB");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u64 pol_stream = l2_policy_evict_first();
+    const u64 pol_keep = l2_policy_evict_last();
+    unsigned long long *bar = bars + warp * STAGES;
+    unsigned char *stage = stages + (size_t)warp * STAGES * kChunkBytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < STAGES; j++) mbar_init(&bar[j], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    u32 phases = 0;
+    chunk_walk4<STAGES>(blockIdx.x * WARPS + warp, num_chunks, gridDim.x * WARPS, lane, bar, stage, phases, data, chunk_row,
+                        rowmap, x4, y4, carry4, head4, pol_stream, pol_keep);
+}
+
+// rows that cross chunk boundaries, four columns at a time (same order of the adds as k_chunk_fixup)
+__global__ void __launch_bounds__(256)
+k_chunk_fixup4(const u32 *__restrict__ fix_row, const u32 *__restrict__ fix_first, const double *__restrict__ carry4,
+               const double *__restrict__ head4, double *__restrict__ y4, u32 num_chunks) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    u32 row = 0xffffffffu, first = 0;
+    if (b < num_chunks) { row = fix_row[b]; first = fix_first[b]; }
+    const bool mine = row != 0xffffffffu;
+    const bool is_long = mine && (b - first > 32u);
+    if (mine && !is_long) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            double s = carry4[(u64)first * 4 + r];
+            for (u32 t = first + 1; t < b; t++) s += carry4[(u64)t * 4 + r];
+            y4[(u64)row * 4 + r] = s + head4[(u64)b * 4 + r];
+        }
+    }
+    u32 todo = __ballot_sync(0xffffffffu, is_long);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const u32 bb = __shfl_sync(0xffffffffu, b, src);
+        const u32 ff = __shfl_sync(0xffffffffu, first, src);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            double s = 0.0;
+            for (u32 t = ff + lane; t < bb; t += 32) s += carry4[(u64)t * 4 + r];
+            s = warp_sum(s);
+            if (lane == src) y4[(u64)row * 4 + r] = s + head4[(u64)b * 4 + r];
+        }
+    }
+}
+
+// x4[i*4 + r] = V[(r) * ld + i] for r < nv (zero for the missing columns of the last batch)
+__global__ void k_pack4(const double *__restrict__ V, u64 ld, u64 n, u32 nv, double *__restrict__ x4) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        D4 o;
+#pragma unroll
+        for (int r = 0; r < 4; r++) o.v[r] = (u32)r < nv ? V[(u64)r * ld + i] : 0.0;
+        st_row4(x4 + i * 4, o);
+    }
+}
+
+// U[r * ldu + i] = y4[i*4 + r] and per-CTA partials of sum U[r]^2 (parts[r * kMaxParts + cta]), r < nv
+__global__ void __launch_bounds__(kVecThreads)
+k_unpack4_sumsq(const double *__restrict__ y4, u64 m, u32 nv, double *__restrict__ U, u64 ldu, double *__restrict__ parts,
+                u32 parts_stride) {
+    __shared__ double sm[4][kVecThreads / 32];
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (; i < m; i += stride) {
+        const double2 a = *reinterpret_cast<const double2 *>(y4 + i * 4), b = *reinterpret_cast<const double2 *>(y4 + i * 4 + 2);
+        const double val[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if ((u32)r < nv) {
+                U[(u64)r * ldu + i] = val[r];
+                acc[r] = fma(val[r], val[r], acc[r]);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const double w = warp_sum(acc[r]);
+        if (lane == 0) sm[r][warp] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < kVecThreads / 32; w++) t += sm[threadIdx.x][w];
+        parts[(u64)threadIdx.x * parts_stride + blockIdx.x] = t;
+    }
+}
+
 int g_chunk_carve[kMaxDevicesTracked][6]; // carve-out (+1) currently set on each instantiation, per device (0 = not yet)
 
 } // namespace
@@ -759,6 +1005,50 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
         if (launches) *launches += 1;
     }
     LAS2_LAUNCH_CHECK();
+}
+
+
+// ---- host side of the 4-RHS product --------------------------------------------------------------------------------
+bool spmm4_supported(const DeviceCsr &A) { return A.chk.active && !A.chk.slabs; }
+
+void Spmm4Work::ensure(const DeviceCsr &A) {
+    const size_t nc = A.chk.num_chunks;
+    if (carry4.size() < 4 * nc) { carry4.alloc(4 * nc); head4.alloc(4 * nc); }
+    if (x4.size() < 4 * A.cols) x4.alloc(4 * A.cols);
+    if (y4.size() < 4 * A.rows) y4.alloc(4 * A.rows);
+    if (parts.size() < 4 * (size_t)kMaxParts) parts.alloc(4 * (size_t)kMaxParts);
+}
+
+// U[r] = A V[r] for r < nv <= 4 (V: vectors ld apart; U: vectors ldu apart) and the per-CTA partials of |U[r]|^2 in
+// work.parts[r * kMaxParts ...] (nparts returned)
+int spmm4(const DeviceCsr &A, const double *V, u64 ld, u32 nv, double *U, u64 ldu, Spmm4Work &work, cudaStream_t s, u64 *launches) {
+    const ChunkStream &K = A.chk;
+    work.ensure(A);
+    const unsigned pgrid = std::max(1u, std::min<unsigned>(cdiv(A.cols, 256), kNumSMs * 8));
+    k_pack4<<<pgrid, 256, 0, s>>>(V, ld, A.cols, nv, work.x4);
+    const size_t smem = chunk_smem_bytes(0);
+    static bool configured[kMaxDevicesTracked];
+    const int dev_slot = current_device_slot();
+    if (!configured[dev_slot]) {
+        LAS2_CUDA(cudaFuncSetAttribute(k_spmm4_chunk<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        LAS2_CUDA(cudaFuncSetAttribute(k_spmm4_chunk<16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1)));
+        configured[dev_slot] = true;
+    }
+    const u32 *rowmap = K.has_empty_rows ? K.rowmap.get() : nullptr;
+    if (K.has_empty_rows) LAS2_CUDA(cudaMemsetAsync(work.y4.get(), 0, 4 * K.rows * sizeof(double), s));
+    const u32 grid = std::min<u32>(kNumSMs, cdiv(K.num_chunks, 16));
+    k_spmm4_chunk<16, 2><<<grid, 16 * 32, smem, s>>>((const uint4 *)K.data, (const u32 *)K.chunk_row, rowmap, work.x4.get(),
+                                                     work.y4.get(), work.carry4.get(), work.head4.get(), K.num_chunks);
+    k_chunk_fixup4<<<cdiv(K.num_chunks, 256), 256, 0, s>>>((const u32 *)K.fix_row, (const u32 *)K.fix_first, work.carry4.get(),
+                                                          work.head4.get(), work.y4.get(), K.num_chunks);
+    u64 g = (A.rows + kVecThreads * 4 - 1) / (kVecThreads * 4);
+    if (g < 1) g = 1;
+    if (g > (u64)kMaxParts) g = kMaxParts;
+    k_unpack4_sumsq<<<(unsigned)g, kVecThreads, 0, s>>>(work.y4.get(), A.rows, nv, U, ldu, work.parts.get(), (u32)kMaxParts);
+    LAS2_LAUNCH_CHECK();
+    if (launches) *launches += 4;
+    return (int)g;
 }
 
 } // namespace las2

@@ -472,7 +472,26 @@ struct Solver {
         DevBuf<double> U((size_t)d * mcols);
         DevBuf<double> S(d);
         DevBuf<double> nrm2(d); // |B_g v_i|^2 per triplet (summed over ranks when sharded)
-        if (!op.comm) {
+        // Matrices on the chunk stream take FOUR triplets per pass over the matrix (k_spmm4_chunk: one 32-byte gather and
+        // one read of the 12 B/nnz stream serve four vectors; every column is bit-identical to its SpMV)
+        static const bool no_spmm = std::getenv("SVDLAS2_NO_SPMM") != nullptr;
+        const bool use4 = spmm4_supported(op.B) && !no_spmm;
+        Spmm4Work w4;
+        if (!op.comm && use4) {
+            for (u64 i0 = 0; i0 < d; i0 += 4) {
+                const u32 nv = (u32)std::min<u64>(4, d - i0);
+                const int np = spmm4(op.B, V.get() + i0 * ld, ld, nv, U.get() + i0 * mcols, mcols, w4, s, &prof.n_kernel_launches);
+                prof.n_spmv += nv;
+                for (u32 r = 0; r < nv; r++)
+                    vec_sigma_scale(U.get() + (i0 + r) * mcols, mcols, PartialSlot{w4.parts.get() + (size_t)r * kMaxParts, np},
+                                    S.get() + i0 + r, s);
+                prof.n_kernel_launches += nv;
+                LAS2_CUDA(cudaEventRecord(ev, s));
+                LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+                LAS2_CUDA(cudaMemcpyAsync(hU + i0 * mcols, U.get() + i0 * mcols, nv * mcols * sizeof(double), cudaMemcpyDeviceToHost,
+                                          copy_stream));
+            }
+        } else if (!op.comm) {
             for (u64 i = 0; i < d; i++) {
                 double *vi = V.get() + i * ld;
                 double *ui = U.get() + i * mcols;
@@ -492,7 +511,17 @@ struct Solver {
             constexpr u64 kBatch = 32;
             for (u64 i0 = 0; i0 < d; i0 += kBatch) {
                 const u64 nb = std::min(kBatch, d - i0);
-                for (u64 i = i0; i < i0 + nb; i++) {
+                for (u64 i = i0; use4 && i < i0 + nb; i += 4) {
+                    const u32 nv = (u32)std::min<u64>(4, i0 + nb - i);
+                    const int np = spmm4(op.B, V.get() + i * ld, ld, nv, U.get() + i * mcols, mcols, w4, s, &prof.n_kernel_launches);
+                    prof.n_spmv += nv;
+                    GatherList g;
+                    g.count = (int)nv;
+                    for (u32 r = 0; r < nv; r++) { g.parts[r] = w4.parts.get() + (size_t)r * kMaxParts; g.nparts[r] = np; }
+                    gather_scalars(g, nrm2.get() + i, s);
+                    prof.n_kernel_launches += 1;
+                }
+                for (u64 i = i0; !use4 && i < i0 + nb; i++) {
                     double *ui = U.get() + i * mcols;
                     spmv(op.B, V.get() + i * ld, ui, s, &prof.n_kernel_launches);
                     prof.n_spmv += 1;

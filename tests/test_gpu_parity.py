@@ -416,3 +416,35 @@ def test_full_size_against_the_recorded_oracle_run(name):
     assert r["alf_head_rel"] <= 1e-9, r
     assert all(v <= r["sketch_bound"] for v in r["sketch_worst"].values()), r
     assert r["sigma_descending"] and r["vt_gram_defect"] < 1e-8 and r["resid_av"] <= 1e-9 and r["resid_atu"] <= 1e-6, r
+
+
+def test_spmm4_columns_equal_the_spmv(las2, monkeypatch):
+    """The sigma / U tail of ritvec (reference src/lib.rs:1839-1859) runs four triplets per pass over the matrix
+    (k_spmm4_chunk): every column must be BIT-identical to the SpMV of that column (same per-lane order, same scan), for
+    ragged rows (empty, short, longer than a chunk) and for 1..4 live columns; |Y[r]|^2 matches to rounding."""
+    import ctypes as C
+    from svdlibrs_b200 import _lib, synthetic
+    monkeypatch.setenv("SVDLAS2_SPMV", "chunk")
+    monkeypatch.setenv("SVDLAS2_SLABS", "0")
+    L = _lib.lib()
+    f64p = C.POINTER(C.c_double)
+    L.svdlas2_test_spmm4.argtypes = [C.c_void_p, C.c_uint32, f64p, f64p, f64p]
+    L.svdlas2_test_spmm4.restype = C.c_int
+    rng = np.random.default_rng(11)
+    A1, _ = synthetic.make("cfg2", scale=0.01)
+    lens = np.array([0, 1, 3, 0, 9, 700, 2, 0, 0, 5000, 1, 1, 8, 255, 256, 257, 0, 33] * 40)
+    rows = np.repeat(np.arange(lens.size), lens)
+    cols = np.concatenate([np.sort(rng.choice(6000, size=n, replace=False)) for n in lens])
+    A2 = sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(lens.size, 6000))
+    for A in (A1, A2):
+        with las2.Operator(A) as op:
+            assert not op.transposed
+            for nv in (4, 1, 3):
+                X = rng.standard_normal((nv, A.shape[1]))
+                Y = np.empty((nv, A.shape[0])); ss = np.empty(nv)
+                rc = L.svdlas2_test_spmm4(op._h, nv, X.ctypes.data_as(f64p), Y.ctypes.data_as(f64p), ss.ctypes.data_as(f64p))
+                assert rc == 0, L.svdlas2_last_error()
+                for r in range(nv):
+                    y = op.opa(X[r])
+                    assert np.array_equal(Y[r], y), (nv, r, np.abs(Y[r] - y).max())
+                    assert abs(ss[r] - y @ y) <= 1e-12 * (y @ y)
