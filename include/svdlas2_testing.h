@@ -38,6 +38,13 @@ SVDLAS2_API int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, in
  * tail computes it.  Returns SVDLAS2_ERR_INVALID_ARGUMENT when the operator's B is not on the chunk stream. */
 SVDLAS2_API int svdlas2_test_spmm4(svdlas2_operator *op, uint32_t nv, const double *X, double *Y, double *sumsq);
 
+/* GPU test hook for the peer-memory exchange kernel of the sharded svd_opb (k_allreduce_epilogue, peer_ring.cu): G ranks
+ * emulated by ONE launch on one GPU (blockIdx.y = rank, G * ctas_per_rank <= 148 so that all CTAs are co-resident).  ys: G
+ * partial vectors of n doubles; out: what every rank ends up with, G vectors of n doubles (must all be equal:
+ * sum_g ys[g] - rnm * qprev, partials added in rank order); dots[g] = rank g's value of out . q.  n % 32 == 0. */
+SVDLAS2_API int svdlas2_test_ring_emulation(int G, uint64_t n, const double *ys, const double *qprev, double rnm,
+                                            const double *q, int two_shot, int ctas_per_rank, double *out, double *dots);
+
 #ifdef __cplusplus
 }
 #endif

@@ -251,8 +251,13 @@ int svdlas2_operator_time_opb(svdlas2_operator *op_, int reps, int flush_l2, dou
             LAS2_CUDA(cudaEventRecord(e0, s));
             spmv(op->B, dx.get(), dt.get(), s);
             LAS2_CUDA(cudaEventRecord(e1, s));
-            spmv(op->BT, dt.get(), dy.get(), s);
-            if (op->comm) op->comm->allreduce_sum(dy.get(), op->N, s);
+            if (op->ring) { // the sharded exchange as it runs inside a Lanczos step: peer-memory sum fused with the epilogue
+                spmv(op->BT, dt.get(), op->ring->y_mine(), s);
+                op->ring->reduce((op->N + 31) / 32 * 32, nullptr, 0.0, nullptr, nullptr, s);
+            } else {
+                spmv(op->BT, dt.get(), dy.get(), s);
+                if (op->comm) op->comm->allreduce_sum(dy.get(), op->N, s);
+            }
             LAS2_CUDA(cudaEventRecord(e2, s));
             LAS2_CUDA(cudaStreamSynchronize(s));
             float a = 0.f, b = 0.f;
@@ -323,6 +328,35 @@ int svdlas2_test_spmm4(svdlas2_operator *op_, uint32_t nv, const double *X, doub
     });
 }
 
+int svdlas2_test_ring_emulation(int G, uint64_t n, const double *ys, const double *qprev, double rnm, const double *q,
+                                int two_shot, int ctas_per_rank, double *out, double *dots) {
+    if (!ys || !out || n == 0 || n % 32) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "bad argument (n must be a multiple of 32)");
+    return guarded([&] {
+        cudaStream_t s;
+        LAS2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        struct SDel { cudaStream_t s; ~SDel() { cudaStreamDestroy(s); } } sdel{s};
+        DevBuf<double> dys((size_t)G * n), dout((size_t)G * n), dq(n), dqp(n), dparts((size_t)G * G * ctas_per_rank + 1), dd(G);
+        LAS2_CUDA(cudaMemcpyAsync(dys.get(), ys, (size_t)G * n * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (q) LAS2_CUDA(cudaMemcpyAsync(dq.get(), q, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (qprev) LAS2_CUDA(cudaMemcpyAsync(dqp.get(), qprev, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        LAS2_CUDA(cudaMemsetAsync(dout.get(), 0xff, (size_t)G * n * sizeof(double), s));
+        int np = 0;
+        ring_emulate(G, n, dys.get(), qprev ? dqp.get() : nullptr, rnm, q ? dq.get() : nullptr, two_shot, ctas_per_rank, dout.get(),
+                     dparts.get(), &np, s);
+        LAS2_CUDA(cudaMemcpyAsync(out, dout.get(), (size_t)G * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (q && dots) {
+            for (int g = 0; g < G; g += 8) { // the canonical sum every consumer kernel forms from the partials
+                GatherList gl;
+                gl.count = std::min(8, G - g);
+                for (int k = 0; k < gl.count; k++) { gl.parts[k] = dparts.get() + (size_t)(g + k) * G * ctas_per_rank; gl.nparts[k] = np; }
+                gather_scalars(gl, dd.get() + g, s);
+            }
+            LAS2_CUDA(cudaMemcpyAsync(dots, dd.get(), G * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        LAS2_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value) {
     Operator *op = reinterpret_cast<Operator *>(op_);
     if (!op || !knob) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
@@ -385,6 +419,15 @@ int svdlas2_operator_create_shard(uint64_t m_global, uint64_t n, uint64_t row_be
                                 op->upload);
         Comm *c = reinterpret_cast<Comm *>(comm);
         op->comm = (c && c->world() > 1) ? c : nullptr;
+        const char *ring_env = std::getenv("SVDLAS2_RING");
+        if (op->comm && !(ring_env && ring_env[0] == '0')) {
+            // collective; every rank reaches the same verdict.  Without peer memory the exchange stays on ncclAllReduce.
+            try { op->ring.reset(PeerRing::create(op->comm, (n + 31) / 32 * 32)); }
+            catch (const Error &e) {
+                op->ring.reset();
+                if (std::getenv("SVDLAS2_TRACE")) fprintf(stderr, "[svdlas2] %s -- using ncclAllReduce\n", e.what());
+            }
+        }
         op->t_upload = wall_now() - t0;
         *out = reinterpret_cast<svdlas2_operator *>(op.release());
     });

@@ -18,7 +18,7 @@ namespace {
 
 struct NcclUniqueId { char internal[128]; };
 using ncclComm_t = void *;
-enum { kNcclSum = 0, kNcclFloat64 = 8 };
+enum { kNcclSum = 0, kNcclInt8 = 0, kNcclFloat64 = 8 };
 
 struct NcclApi {
     int (*GetUniqueId)(NcclUniqueId *) = nullptr;
@@ -94,6 +94,22 @@ Comm::~Comm() {
 void Comm::allreduce_sum(double *buf, uint64_t n, cudaStream_t s) {
     if (world_ == 1) return;
     check(api().AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, nccl_comm_, s), "ncclAllReduce");
+}
+
+void Comm::allgather_host_bytes(const void *mine, void *all, size_t bytes_each) {
+    if (world_ == 1) { std::memcpy(all, mine, bytes_each); return; }
+    void *d = nullptr;
+    LAS2_CUDA(cudaMalloc(&d, bytes_each * (size_t)world_));
+    cudaError_t e = cudaMemcpy(static_cast<char *>(d) + (size_t)rank_ * bytes_each, mine, bytes_each, cudaMemcpyHostToDevice);
+    int rc = 0;
+    if (e == cudaSuccess) {
+        rc = api().AllGather(static_cast<char *>(d) + (size_t)rank_ * bytes_each, d, bytes_each, kNcclInt8, nccl_comm_, (cudaStream_t)0);
+        if (rc == 0) e = cudaStreamSynchronize((cudaStream_t)0);
+        if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(all, d, bytes_each * (size_t)world_, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    check(rc, "ncclAllGather (host bytes)");
+    LAS2_CUDA(e);
 }
 
 void Comm::allgather_ranges(double *buf, const uint64_t *offs, cudaStream_t s) {

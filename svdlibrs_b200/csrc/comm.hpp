@@ -22,6 +22,8 @@ class Comm {
     // in-place all-gather of row ranges: rank g owns buf[offs[g] .. offs[g+1]) (offs has world()+1 entries, in doubles)
     // and every rank ends up with all of them (one ncclAllGather through an internal staging buffer)
     void allgather_ranges(double *buf, const uint64_t *offs, cudaStream_t s);
+    // host-side exchange of a few bytes per rank (set-up of the peer-memory ring): all[h * bytes_each ..] = rank h's block
+    void allgather_host_bytes(const void *mine, void *all, size_t bytes_each);
 
   private:
     Comm() = default;

@@ -55,7 +55,8 @@ struct Solver {
     // device
     DevBuf<double> Q;
     u64 qcap = 0, qused = 0;
-    DevBuf<double> r, xs, t;
+    DevBuf<double> r_own, xs, t;
+    struct RPtr { double *p = nullptr; double *get() const { return p; } } r; // w0: the ring's buffer in a sharded run
     DevBuf<double> parts;
     PartialSlot slot[8];
     PinnedBuf<double> hs;
@@ -74,7 +75,8 @@ struct Solver {
         : op(o), s(o.stream), N(o.N), M(o.M), ld(round_up(o.N, 32)), dims(dimensions), iters(iterations),
           eps1(kEps * std::sqrt((double)o.N)) {
         std::memset(&prof, 0, sizeof prof);
-        r.alloc(ld); xs.alloc(ld); t.alloc(M ? M : 1);
+        if (op.ring) { r.p = op.ring->r_mine(); } else { r_own.alloc(ld); r.p = r_own.get(); }
+        xs.alloc(ld); t.alloc(M ? M : 1);
         LAS2_CUDA(cudaMemsetAsync(r.get(), 0, ld * sizeof(double), s));
         LAS2_CUDA(cudaMemsetAsync(xs.get(), 0, ld * sizeof(double), s));
         parts.alloc(8 * (size_t)kMaxParts);
@@ -124,6 +126,23 @@ struct Solver {
             LAS2_CUDA(cudaEventRecord(e0, s));
         }
         op.opb(x, y, t.get(), &prof.n_kernel_launches);
+        if (op.profile) {
+            LAS2_CUDA(cudaEventRecord(e1, s));
+            opb_events.emplace_back(e0, e1);
+        }
+        prof.n_opb += 1;
+        prof.n_spmv += 2;
+    }
+
+    void opb_step(const double *x, const double *qprev, double rnm, PartialSlot &alf) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (op.profile) {
+            LAS2_CUDA(cudaEventCreate(&e0)); LAS2_CUDA(cudaEventCreate(&e1));
+            LAS2_CUDA(cudaEventRecord(e0, s));
+        }
+        PartialSlot out = alf;
+        op.opb_step(x, qprev, rnm, r.get(), t.get(), &out, ld, &prof.n_kernel_launches);
+        alf = out; // (the ring hands out its own partial buffer)
         if (op.profile) {
             LAS2_CUDA(cudaEventRecord(e1, s));
             opb_events.emplace_back(e0, e1);
@@ -265,11 +284,11 @@ struct Solver {
             const double rn = *rnm;
             vec_scale(q(j), r.get(), 1.0 / rn, ld, s);
             qused = j + 1;
-            opb(q(j), r.get());
             int ns = 0; // slots in use for this step
-            vec_axpy_dot(r.get(), q(j - 1), Coef::value(rn), q(j), ld, slot[ns], s); // r -= rnm q_{j-1} ; alf = r.q_j
-            prof.n_kernel_launches += 2;
-            const int s_alf = ns++;
+            // r = B'B q_j - rnm q_{j-1} ; alf = r . q_j  (sharded: the all-reduce, the update and the dot are ONE kernel)
+            // (slot 7 is reserved for alf: in a sharded run it points into the ring's partial buffer)
+            constexpr int s_alf = 7;
+            opb_step(q(j), q(j - 1), rn, slot[s_alf]);
             if (j <= kMaxLL) {
                 // |alf[j-1]| > 4 |alf[j]| decides ll only while j <= MAXLL (:1282): needs alf[j] now
                 double a;
@@ -569,8 +588,33 @@ Operator::~Operator() {
 
 void Operator::opb(const double *x, double *y, double *t, u64 *launches) {
     spmv(B, x, t, stream, launches);
+    if (ring) {
+        spmv(BT, t, ring->y_mine(), stream, launches);
+        ring->reduce((N + 31) / 32 * 32, nullptr, 0.0, nullptr, nullptr, stream);
+        if (launches) *launches += 1;
+        if (y != ring->r_mine())
+            LAS2_CUDA(cudaMemcpyAsync(y, ring->r_mine(), N * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        return;
+    }
     spmv(BT, t, y, stream, launches);
     if (comm) comm->allreduce_sum(y, N, stream);
+}
+
+void Operator::opb_step(const double *x, const double *qprev, double rnm, double *r, double *t, PartialSlot *alf, u64 ld,
+                        u64 *launches) {
+    if (ring) {
+        if (r != ring->r_mine()) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "opb_step: r must be the ring's buffer");
+        spmv(B, x, t, stream, launches);
+        spmv(BT, t, ring->y_mine(), stream, launches);
+        ring->reduce(ld, qprev, rnm, x, alf, stream); // sum over ranks + r -= rnm qprev + partials of r . x, one kernel
+        if (launches) *launches += 1;
+        return;
+    }
+    opb(x, r, t, launches);
+    if (qprev) {
+        vec_axpy_dot(r, qprev, Coef::value(rnm), x, ld, *alf, stream);
+        if (launches) *launches += 1;
+    }
 }
 
 void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interval[2], double kappa,
@@ -650,6 +694,7 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
     sv.prof.t_ritvec = wall() - tr0;
     sv.prof.t_imtql2 = t_imtql2;
 
+    if (op.ring) ring_quiesce(*op.ring, op.stream); // no rank touches a peer's memory after its solve has returned
     LAS2_CUDA(cudaEventRecord(ev_end, op.stream));
     LAS2_CUDA(cudaEventSynchronize(ev_end));
     {

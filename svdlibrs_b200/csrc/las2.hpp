@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "comm.hpp"
+#include "peer_ring.cuh"
 #include "device_csr.cuh"
 #include "host_math.hpp"
 #include "vecops.cuh"
@@ -25,6 +26,9 @@ struct Operator {
     u64 row_begin = 0;
     DeviceCsr B, BT; // BT is N x M (local)
     Comm *comm = nullptr; // borrowed; null on a single GPU
+    // the exchange step of a sharded opb over NVLink peer memory, fused with the first update of the Lanczos step
+    // (peer_ring.cuh); null on a single GPU, when peer memory cannot be mapped, or with SVDLAS2_RING=0 (then: ncclAllReduce)
+    std::unique_ptr<PeerRing> ring;
     // scratch for opa/opb/time_opb
     DevBuf<double> tmp_m, tmp_x, tmp_y;
     DevBuf<char> l2_flush;
@@ -39,6 +43,9 @@ struct Operator {
     u64 opb_bytes() const { return B.spmv_bytes() + BT.spmv_bytes(); } // 24 Z + 20 (M + N) + 8
     // y = B'(B x) on the stream; x, y device N-vectors (y != x); t scratch of M doubles
     void opb(const double *x, double *y, double *t, u64 *launches);
+    // r = B'(B x) - rnm * qprev with the partials of r . x in *alf (reference :1276-1278 in one go); qprev == nullptr: r =
+    // B'(B x) only.  With a ring, r MUST be ring->r_mine() (the peers push their slices into it).
+    void opb_step(const double *x, const double *qprev, double rnm, double *r, double *t, PartialSlot *alf, u64 ld, u64 *launches);
 };
 
 struct SolveOutput; // svdlas2_result with owned buffers (abi.cu)

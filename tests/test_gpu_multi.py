@@ -28,13 +28,19 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("shard_purge_mb", ["", "0"])
-@pytest.mark.parametrize("workload,scale,dims", [("cfg2", 0.05, 30), ("cfg3", 0.01, 20)])
-def test_sharded_solve_matches_single_gpu_and_oracle(workload, scale, dims, shard_purge_mb, monkeypatch):
+@pytest.mark.parametrize("workload,scale,dims,shard_purge_mb,ring", [
+    ("cfg2", 0.05, 30, "", "1"), ("cfg2", 0.05, 30, "0", "1"), ("cfg3", 0.01, 20, "", "1"), ("cfg3", 0.01, 20, "0", "two-shot"),
+    ("cfg2", 0.05, 30, "", "two-shot"), ("cfg2", 0.05, 30, "", "0")])
+def test_sharded_solve_matches_single_gpu_and_oracle(workload, scale, dims, shard_purge_mb, ring, monkeypatch):
     """shard_purge_mb = "0": every reorthogonalisation sweep is split by rows over the ranks (all-reduce of the
     coefficients + all-gather of the updated pair) instead of only the big ones"""
     if n_gpus() < 2:
         pytest.skip("needs at least 2 GPUs")
+    # the exchange step: "1" = peer-memory kernel fused with the epilogue (one-shot at these sizes), "two-shot" = the same
+    # kernel forced into its reduce-scatter + push form, "0" = ncclAllReduce + separate update kernel
+    monkeypatch.setenv("SVDLAS2_RING", "0" if ring == "0" else "1")
+    if ring == "two-shot":
+        monkeypatch.setenv("SVDLAS2_RING_TWO_SHOT_KB", "0")
     if shard_purge_mb:
         monkeypatch.setenv("SVDLAS2_SHARD_PURGE_MB", shard_purge_mb)
         monkeypatch.setenv("SVDLAS2_SHARD_RITZ_GFLOP", "0")  # and the Ritz contraction as well

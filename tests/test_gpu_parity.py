@@ -448,3 +448,34 @@ def test_spmm4_columns_equal_the_spmv(las2, monkeypatch):
                     y = op.opa(X[r])
                     assert np.array_equal(Y[r], y), (nv, r, np.abs(Y[r] - y).max())
                     assert abs(ss[r] - y @ y) <= 1e-12 * (y @ y)
+
+
+@pytest.mark.parametrize("G,two_shot,ctas", [(2, 0, 8), (4, 0, 16), (8, 0, 18), (2, 1, 8), (4, 1, 16), (8, 1, 18), (3, 1, 5)])
+def test_peer_ring_kernel_emulated_ranks(las2, G, two_shot, ctas):
+    """The exchange step of the sharded svd_opb (k_allreduce_epilogue, peer_ring.cu; reference src/lib.rs:835-836 + :1277-1278
+    in one kernel): G ranks emulated by ONE launch on one GPU (flag barriers, rank-ordered sum, epilogue r -= rnm q_{j-1},
+    partials of r . q_j, two-shot pushes).  Every rank must end up with the SAME BITS, equal to the partials added in rank
+    order; the dot products must be bit-identical across ranks."""
+    import ctypes as C
+    from svdlibrs_b200 import _lib
+    L = _lib.lib()
+    f64p = C.POINTER(C.c_double)
+    L.svdlas2_test_ring_emulation.argtypes = [C.c_int, C.c_uint64, f64p, f64p, C.c_double, f64p, C.c_int, C.c_int, f64p, f64p]
+    L.svdlas2_test_ring_emulation.restype = C.c_int
+    rng = np.random.default_rng(100 + G)
+    n = 32 * 1237
+    ys, qprev, q, rnm = rng.standard_normal((G, n)), rng.standard_normal(n), rng.standard_normal(n), 0.37
+    out, dots = np.empty((G, n)), np.empty(G)
+    p = lambda a: a.ctypes.data_as(f64p)
+    for with_epilogue in (True, False):
+        rc = L.svdlas2_test_ring_emulation(G, n, p(ys), p(qprev) if with_epilogue else None, rnm, p(q), two_shot, ctas, p(out), p(dots))
+        assert rc == 0, L.svdlas2_last_error()
+        want = ys[0].copy()
+        for h in range(1, G):
+            want = want + ys[h]                       # rank order, one rounding per add
+        if with_epilogue:
+            want = want + (-rnm) * qprev              # rounded product, rounded sum (svd_daxpy)
+        for g in range(G):
+            assert np.array_equal(out[g], want), (g, np.abs(out[g] - want).max())
+        assert np.all(dots == dots[0])
+        assert abs(dots[0] - want @ q) <= 1e-11 * np.linalg.norm(want) * np.linalg.norm(q)
