@@ -38,6 +38,11 @@ SVDLAS2_API int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, in
  * tail computes it.  Returns SVDLAS2_ERR_INVALID_ARGUMENT when the operator's B is not on the chunk stream. */
 SVDLAS2_API int svdlas2_test_spmm4(svdlas2_operator *op, uint32_t nv, const double *X, double *Y, double *sumsq);
 
+/* How the upload laid the operator out: out[0] = 1 when the N side was relabelled by popularity, out[1] = share of B's column
+ * indices inside the shared-memory prefix (hot_fraction), out[2] = size of that prefix, out[3] / out[4] = mode of B's / B''s
+ * first stream and out[5] of B''s second one (-1 none, 0 plain, 1 plain + hot prefix, 2 slab-local, 3 wide slabs),
+ * out[6] = first row of B''s second stream, out[7] = number of slabs of B''s first stream. */
+SVDLAS2_API int svdlas2_test_operator_layout(const svdlas2_operator *op, double out[8]);
 /* GPU test hook for the peer-memory exchange kernel of the sharded svd_opb (k_allreduce_epilogue, peer_ring.cu): G ranks
  * emulated by ONE launch on one GPU (blockIdx.y = rank, G * ctas_per_rank <= 148 so that all CTAs are co-resident).  ys: G
  * partial vectors of n doubles; out: what every rank ends up with, G vectors of n doubles (must all be equal:

@@ -72,7 +72,7 @@ Operator *create_operator(int format, u64 nrows, u64 ncols, u64 nnz, const u64 *
     op->M_global = op->M = op->transposed ? ncols : nrows;
     op->N = op->transposed ? nrows : ncols;
     HostSparse A{format, nrows, ncols, nnz, a, b, values};
-    build_operator(A, op->transposed, op->stream, op->B, op->BT, op->upload);
+    build_operator(A, op->transposed, op->stream, op->B, op->BT, op->upload, op->relabel);
     op->t_upload = wall_now() - t0;
     return op.release();
 }
@@ -206,10 +206,26 @@ int svdlas2_operator_opa(svdlas2_operator *op_, const double *x, double *y, int 
         const bool use_b = (transposed != 0) == op->transposed; // A x -> B x when !op.transposed ; A'x -> B x when op.transposed
         const DeviceCsr &Mx = use_b ? op->B : op->BT;
         DevBuf<double> dx(Mx.cols ? Mx.cols : 1), dy(Mx.rows ? Mx.rows : 1);
+        // the N side lives in the relabelled order on the device: permute on the way in (B x) or out (B' t)
+        const std::vector<u32> &n2o = op->relabel.h_new2old;
+        std::vector<double> hx;
+        if (op->relabel.active && use_b) {
+            hx.resize(Mx.cols);
+            for (u64 i = 0; i < Mx.cols; i++) hx[i] = x[n2o[i]];
+            x = hx.data();
+        }
         LAS2_CUDA(cudaMemcpyAsync(dx.get(), x, Mx.cols * sizeof(double), cudaMemcpyHostToDevice, op->stream));
+        LAS2_CUDA(cudaStreamSynchronize(op->stream));
         // poison the output (NaN pattern): a row the kernel forgets to write must not look plausible
         LAS2_CUDA(cudaMemsetAsync(dy.get(), 0xff, Mx.rows * sizeof(double), op->stream));
         spmv(Mx, dx.get(), dy.get(), op->stream);
+        if (op->relabel.active && !use_b) {
+            std::vector<double> hy(Mx.rows);
+            LAS2_CUDA(cudaMemcpyAsync(hy.data(), dy.get(), Mx.rows * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
+            LAS2_CUDA(cudaStreamSynchronize(op->stream));
+            for (u64 i = 0; i < Mx.rows; i++) y[n2o[i]] = hy[i];
+            return;
+        }
         LAS2_CUDA(cudaMemcpyAsync(y, dy.get(), Mx.rows * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
         LAS2_CUDA(cudaStreamSynchronize(op->stream));
     });
@@ -221,10 +237,19 @@ int svdlas2_operator_opb(svdlas2_operator *op_, const double *x, double *y) {
     return guarded([&] {
         LAS2_CUDA(cudaSetDevice(op->device));
         DevBuf<double> dx(op->N ? op->N : 1), dy(op->N ? op->N : 1), dt(op->M ? op->M : 1);
+        const std::vector<u32> &n2o = op->relabel.h_new2old;
+        std::vector<double> hx, hy;
+        if (op->relabel.active) {
+            hx.resize(op->N); hy.resize(op->N);
+            for (u64 i = 0; i < op->N; i++) hx[i] = x[n2o[i]];
+            x = hx.data();
+        }
         LAS2_CUDA(cudaMemcpyAsync(dx.get(), x, op->N * sizeof(double), cudaMemcpyHostToDevice, op->stream));
         op->opb(dx.get(), dy.get(), dt.get(), nullptr);
-        LAS2_CUDA(cudaMemcpyAsync(y, dy.get(), op->N * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
+        LAS2_CUDA(cudaMemcpyAsync(op->relabel.active ? hy.data() : y, dy.get(), op->N * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
         LAS2_CUDA(cudaStreamSynchronize(op->stream));
+        if (op->relabel.active)
+            for (u64 i = 0; i < op->N; i++) y[n2o[i]] = hy[i];
     });
 }
 
@@ -304,6 +329,25 @@ int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, int device, do
     });
 }
 
+int svdlas2_test_operator_layout(const svdlas2_operator *op_, double out[8]) {
+    const Operator *op = reinterpret_cast<const Operator *>(op_);
+    if (!op || !out) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
+    auto mode = [](const ChunkStream &K) -> double {
+        if (!K.active) return -1.0;
+        if (K.slabs) return K.slab_local ? 2.0 : 3.0;
+        return K.hot_entries > 0 ? 1.0 : 0.0;
+    };
+    out[0] = op->relabel.active ? 1.0 : 0.0;
+    out[1] = op->B.hot_fraction;
+    out[2] = (double)op->B.hot_entries;
+    out[3] = mode(op->B.chk);
+    out[4] = mode(op->BT.chk);
+    out[5] = mode(op->BT.chk2);
+    out[6] = (double)op->BT.chk2.row0;
+    out[7] = (double)op->BT.chk.nslabs;
+    return SVDLAS2_OK;
+}
+
 int svdlas2_test_spmm4(svdlas2_operator *op_, uint32_t nv, const double *X, double *Y, double *sumsq) {
     Operator *op = reinterpret_cast<Operator *>(op_);
     if (!op || !X || !Y || nv < 1 || nv > 4) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "bad argument");
@@ -314,7 +358,15 @@ int svdlas2_test_spmm4(svdlas2_operator *op_, uint32_t nv, const double *X, doub
         const u64 N = op->N, M = op->M, ld = (N + 31) / 32 * 32;
         DevBuf<double> dx((size_t)nv * ld), dy((size_t)nv * M), ds(nv);
         LAS2_CUDA(cudaMemsetAsync(dx.get(), 0, (size_t)nv * ld * sizeof(double), s));
+        std::vector<double> hx;
+        if (op->relabel.active) {
+            hx.resize((size_t)nv * N);
+            for (uint32_t r = 0; r < nv; r++)
+                for (u64 i = 0; i < N; i++) hx[(size_t)r * N + i] = X[(size_t)r * N + op->relabel.h_new2old[i]];
+            X = hx.data();
+        }
         LAS2_CUDA(cudaMemcpy2DAsync(dx.get(), ld * sizeof(double), X, N * sizeof(double), N * sizeof(double), nv, cudaMemcpyHostToDevice, s));
+        LAS2_CUDA(cudaStreamSynchronize(s));
         LAS2_CUDA(cudaMemsetAsync(dy.get(), 0xff, (size_t)nv * M * sizeof(double), s));
         Spmm4Work w4;
         const int np = spmm4(op->B, dx.get(), ld, nv, dy.get(), M, w4, s);
@@ -415,10 +467,10 @@ int svdlas2_operator_create_shard(uint64_t m_global, uint64_t n, uint64_t row_be
         op->M = row_end - row_begin;
         op->row_begin = row_begin;
         op->N = n;
-        build_operator_from_csr(op->M, n, local_nnz, local_offsets, local_indices, values, op->stream, op->B, op->BT,
-                                op->upload);
         Comm *c = reinterpret_cast<Comm *>(comm);
         op->comm = (c && c->world() > 1) ? c : nullptr;
+        build_operator_from_csr(op->M, n, local_nnz, local_offsets, local_indices, values, op->stream, op->B, op->BT,
+                                op->upload, op->relabel, op->comm);
         const char *ring_env = std::getenv("SVDLAS2_RING");
         if (op->comm && !(ring_env && ring_env[0] == '0')) {
             // collective; every rank reaches the same verdict.  Without peer memory the exchange stays on ncclAllReduce.

@@ -142,11 +142,11 @@ __global__ void k_chunk_flags(const u32 *__restrict__ cstart, u32 nc, uint4 *__r
 // ---- slab mode ----
 
 // cnt[slab * rows + row] += 1 for every non-zero (integer atomics: the result does not depend on the order)
-__global__ void k_piece_count(const u32 *__restrict__ idx, const u32 *__restrict__ rowid, u64 nnz, u64 rows,
+__global__ void k_piece_count(const u32 *__restrict__ idx, const u32 *__restrict__ rowid, u64 nnz, u64 rows, u32 width,
                               u32 *__restrict__ cnt) {
     u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (; k < nnz; k += stride) atomicAdd(&cnt[(u64)(idx[k] / kSlabWidth) * rows + rowid[k]], 1u);
+    for (; k < nnz; k += stride) atomicAdd(&cnt[(u64)(idx[k] / width) * rows + rowid[k]], 1u);
 }
 
 // ne[v] = cnt[v] > 0 (ne has one more slot, set to 0, so that the scan leaves the total there)
@@ -170,16 +170,16 @@ __global__ void k_piece_starts(const u32 *__restrict__ pos, const u32 *__restric
 // ranked scatter into the (slab, row, column) order: inside a row the entries of one slab are contiguous (columns
 // ascend), so the rank of entry k inside its piece is k minus the position of the piece's first entry in the row
 __global__ void k_slab_scatter(const u32 *__restrict__ off, const u32 *__restrict__ idx, const double *__restrict__ val,
-                               const u32 *__restrict__ rowid, u64 nnz, u64 rows, const u32 *__restrict__ pos,
-                               const u32 *__restrict__ shift, uint4 *__restrict__ data) {
+                               const u32 *__restrict__ rowid, u64 nnz, u64 rows, u32 width, int local,
+                               const u32 *__restrict__ pos, const u32 *__restrict__ shift, uint4 *__restrict__ data) {
     double *dv = reinterpret_cast<double *>(data);
     u32 *di = reinterpret_cast<u32 *>(data);
     u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (; k < nnz; k += stride) {
         const u32 c = idx[k], r = rowid[k];
-        const u32 sl = c / kSlabWidth;
-        const u32 first_col = sl * kSlabWidth;
+        const u32 sl = c / width;
+        const u32 first_col = sl * width;
         u32 lo = off[r], hi = (u32)k; // lower_bound of first_col in idx[off[r] .. k]
         while (lo < hi) {
             const u32 mid = lo + ((hi - lo) >> 1);
@@ -187,7 +187,7 @@ __global__ void k_slab_scatter(const u32 *__restrict__ off, const u32 *__restric
         }
         const u64 e = (u64)pos[(u64)sl * rows + r] + shift[sl] + ((u32)k - lo);
         dv[chunk_val_slot(e)] = val[k];
-        di[chunk_idx_slot(e)] = c - first_col;
+        di[chunk_idx_slot(e)] = local ? c - first_col : c;
     }
 }
 
@@ -813,21 +813,28 @@ void finalize_chunks(ChunkStream &K, const u32 *cstart, const u32 *rowmap, u32 n
 }
 
 // Slab mode.  Returns false (leaving K untouched apart from scratch) when the matrix is too sparse per piece.
-bool build_slab_stream(DeviceCsr &X, ChunkStream &K, bool force, cudaStream_t s, UploadStats &st) {
+// A CSR matrix (or a row range of one) as the builders see it: offsets rebased to 0, arrays borrowed.
+struct CsrView {
+    u64 rows, cols, nnz;
+    const u32 *off, *idx;
+    const double *val;
+};
+
+// Slab-ordered stream.  local: slab-local column indices, width kSlabWidth (all gathers from shared memory); otherwise global
+// indices and any width (gathers through L1, the order only blocks the gathered vector for L2).  Returns false (leaving K
+// untouched apart from scratch) when a (slab, row) piece holds fewer than `min_per_piece` entries on average.
+bool build_slab_stream(const CsrView &X, ChunkStream &K, u32 width, bool local, bool force, double min_per_piece, cudaStream_t s,
+                       UploadStats &st) {
     const u64 rows = X.rows, nnz = X.nnz;
-    const u32 nslabs = cdiv(X.cols, kSlabWidth);
+    const u32 nslabs = cdiv(X.cols, width);
     const u64 npieces = (u64)nslabs * rows;
     if (nslabs < 2 || npieces + 1 >= ((u64)1 << 28)) return false;
-    const double min_per_piece = 4.0;
 
     DevBuf<u32> rowid(nnz);
-    {
-        // rowid[k] = row of entry k (upper_bound over the offsets)
-        expand_row_ids(X.off, (u32)rows, nnz, rowid, s, st);
-    }
+    expand_row_ids(X.off, (u32)rows, nnz, rowid, s, st);
     DevBuf<u32> pos(npieces + 1);
     LAS2_CUDA(cudaMemsetAsync(pos.get(), 0, (npieces + 1) * sizeof(u32), s));
-    k_piece_count<<<grid_for(nnz, 256 * 4), 256, 0, s>>>(X.idx, rowid, nnz, rows, pos);
+    k_piece_count<<<grid_for(nnz, 256 * 4), 256, 0, s>>>(X.idx, rowid, nnz, rows, width, pos);
     LAS2_LAUNCH_CHECK();
     K.piece_id.alloc(npieces + 1);
     k_piece_nonempty<<<grid_for(npieces + 1, 256 * 4), 256, 0, s>>>(pos, npieces, K.piece_id);
@@ -866,7 +873,7 @@ bool build_slab_stream(DeviceCsr &X, ChunkStream &K, bool force, cudaStream_t s,
     LAS2_LAUNCH_CHECK();
     K.data.alloc(((size_t)num_chunks + 1) * (kChunkBytes / 16));
     LAS2_CUDA(cudaMemsetAsync(K.data.get(), 0, ((size_t)num_chunks + 1) * kChunkBytes, s)); // padding: value 0, column 0
-    k_slab_scatter<<<grid_for(nnz, 256 * 2), 256, 0, s>>>(X.off, X.idx, X.val, rowid, nnz, rows, pos, dshift, K.data);
+    k_slab_scatter<<<grid_for(nnz, 256 * 2), 256, 0, s>>>(X.off, X.idx, X.val, rowid, nnz, rows, width, local ? 1 : 0, pos, dshift, K.data);
     LAS2_LAUNCH_CHECK();
     st.launches += 2;
     finalize_chunks(K, cstart, nullptr, nc, num_chunks, s, st);
@@ -882,13 +889,15 @@ bool build_slab_stream(DeviceCsr &X, ChunkStream &K, bool force, cudaStream_t s,
     LAS2_CUDA(cudaMemsetAsync(K.part.get(), 0, (size_t)nc * sizeof(double), s));
     LAS2_CUDA(cudaStreamSynchronize(s)); // scratch and host vectors go out of scope
     K.slabs = true;
+    K.slab_local = local;
+    K.slab_width = width;
     K.nslabs = nslabs;
     K.nonempty_rows = nc;
     K.stream_bytes = (u64)num_chunks * kChunkBytes + 4 * (u64)num_chunks + 16 * (u64)nc + 4 * (npieces + 1) + 8 * X.cols * 2 + 8 * rows;
     return true;
 }
 
-void build_plain_stream(DeviceCsr &X, ChunkStream &K, cudaStream_t s, UploadStats &st) {
+void build_plain_stream(const CsrView &X, ChunkStream &K, cudaStream_t s, UploadStats &st) {
     const u32 rows = (u32)X.rows, nnz = (u32)X.nnz;
     const u32 num_chunks = nnz / kChunkNnz + 1; // always room for the sentinel row start at element nnz
     const u64 padded = (u64)num_chunks * kChunkNnz;
@@ -905,7 +914,7 @@ void build_plain_stream(DeviceCsr &X, ChunkStream &K, cudaStream_t s, UploadStat
     K.nonempty_rows = nc;
     K.has_empty_rows = nc != rows;
     DevBuf<u32> cstart_buf;
-    const u32 *cstart = X.off.get(); // identity numbering: the row offsets are the starts, off[rows] = nnz the sentinel
+    const u32 *cstart = X.off; // identity numbering: the row offsets are the starts, off[rows] = nnz the sentinel
     if (K.has_empty_rows) {
         cstart_buf.alloc((size_t)nc + 1);
         K.rowmap.alloc(std::max<u32>(nc, 1));
@@ -923,15 +932,46 @@ void build_plain_stream(DeviceCsr &X, ChunkStream &K, cudaStream_t s, UploadStat
     K.stream_bytes = (u64)num_chunks * kChunkBytes + 4 * (u64)num_chunks + 8 * X.cols + 8 * X.rows;
 }
 
+__global__ void k_rebase_offsets(const u32 *__restrict__ off, u32 r0, u32 n, u32 *__restrict__ out) {
+    const u32 base = off[r0];
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (; i <= n; i += stride) out[i] = off[r0 + i] - base;
+}
+
+constexpr u64 kWideSlabWidth = (u64)1 << 20;        // 8 MB of the gathered vector per wide slab
+constexpr u64 kWideSlabMinCols = (u64)3 << 19;      // gathered vectors beyond 12 MB are blocked
+constexpr u64 kSlabMinNnz = 20000000;               // per-launch cost of the slab modes (slice loads, reduce kernel)
+
+int env_int(const char *name, int dflt) { const char *e = std::getenv(name); return (e && e[0]) ? std::atoi(e) : dflt; }
+
+// the best stream for one row range: slab-local when forced / dense enough per piece, else wide slabs for a huge gathered
+// vector, else the plain stream (with the matrix's hot prefix, if it has one)
+void build_range(const CsrView &V, ChunkStream &K, u32 hot_entries, bool try_local, bool force_local, cudaStream_t s, UploadStats &st) {
+    K = ChunkStream();
+    bool done = false;
+    const int wide_mode = env_int("SVDLAS2_WIDE_SLABS", -1); // -1 auto, 0 never, 1 whenever there are >= 2 slabs
+    if (try_local || force_local) done = build_slab_stream(V, K, kSlabWidth, true, force_local, 4.0, s, st);
+    if (!done && wide_mode != 0 && hot_entries == 0 && V.cols >= 2 * kWideSlabWidth &&
+        (wide_mode == 1 || (V.cols >= kWideSlabMinCols && V.nnz >= kSlabMinNnz))) {
+        K = ChunkStream();
+        done = build_slab_stream(V, K, (u32)kWideSlabWidth, false, wide_mode == 1, 4.0, s, st);
+    }
+    if (!done) { K = ChunkStream(); build_plain_stream(V, K, s, st); K.hot_entries = hot_entries; }
+    K.rows = V.rows; K.cols = V.cols;
+    K.active = true;
+}
+
 } // namespace
 
-// Builds X.chk from the natural CSR arrays of X (device-side, deterministic).
+// Builds X.chk (and X.chk2) from the natural CSR arrays of X (device-side, deterministic).
 void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
-    ChunkStream &K = X.chk;
-    K = ChunkStream();
+    X.chk = ChunkStream();
+    X.chk2 = ChunkStream();
     // SVDLAS2_SPMV: unset = this format for matrices large enough to fill the persistent kernel; "chunk" = always;
-    // anything else (e.g. "tile", "blocked") = never (the older kernels stay reachable for comparison).
+    // anything else (e.g. "tile") = never (the tile kernels stay reachable for comparison).
     // SVDLAS2_SLABS: unset = slab mode where a (slab, row) piece holds >= 4 entries on average; 0 = never; 1 = always.
+    // SVDLAS2_SPLIT: unset / 1 = a frequency-ordered B' is cut into heavy rows (slab mode) and light rows; 0 = never.
     const char *want = std::getenv("SVDLAS2_SPMV");
     const bool force = want && std::string(want) == "chunk";
     if (want && want[0] && !force) return;
@@ -940,26 +980,50 @@ void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
     if (X.cols >= kChunkFlag || X.rows >= kChunkFlag || X.nnz + 2 * (u64)kChunkNnz >= ((u64)1 << 32)) return;
     const char *sl = std::getenv("SVDLAS2_SLABS");
     const char slab_mode = (sl && sl[0]) ? sl[0] : 'a';
-    bool done = false;
-    // Slabs only when the hot prefix cannot do the job (cfg 2: B, 65 % of whose gathers hit the first 8192 entries of
-    // x, runs 0.12 ms with the prefix and 0.19 ms in slab mode; B', whose gathered vector t has no popular prefix,
-    // 0.19 ms without slabs and 0.15 ms with them).
-    // And only for matrices (shards) big enough to amortise the per-launch cost of the mode (slice loads, the reduce
-    // kernel: ~20 us against ~1.3 ps saved per non-zero).
-    if (slab_mode == '1' || (slab_mode != '0' && X.hot_entries == 0 && X.nnz >= (u64)20000000))
-        done = build_slab_stream(X, K, slab_mode == '1', s, st);
-    if (!done) { K = ChunkStream(); build_plain_stream(X, K, s, st); }
-    K.rows = X.rows; K.cols = X.cols;
-    K.active = true;
+    const CsrView whole{X.rows, X.cols, X.nnz, X.off.get(), X.idx.get(), X.val.get()};
+    // Slabs only when the hot prefix cannot do the job (cfg 2: B, 65 % of whose gathers hit the first 8192 entries of x,
+    // runs 0.12 ms with the prefix and 0.19 ms in slab mode; B', whose gathered vector t has no popular prefix, 0.19 ms
+    // without slabs and 0.15 ms with them), and only for matrices (shards) big enough to amortise the mode's fixed cost.
+    const bool slab_candidate = slab_mode == '1' || (slab_mode != '0' && X.hot_entries == 0 && X.nnz >= kSlabMinNnz);
+
+    // ---- split of a frequency-ordered B': rows whose (slab, row) pieces are dense enough run in slab-local mode, the light
+    // rows apart (wide slabs for a huge gathered vector, else plain): at cfg 4 the 35 k heaviest rows of B' hold 56 % of
+    // the non-zeros with >= 6 entries per piece, while the whole matrix averages < 1 ----
+    if (X.rows_sorted_desc && slab_candidate && slab_mode != '1' && env_int("SVDLAS2_SPLIT", 1) != 0 && X.rows >= 4096) {
+        const u32 nslabs16 = cdiv(X.cols, kSlabWidth);
+        std::vector<u32> off(X.rows + 1);
+        LAS2_CUDA(cudaMemcpyAsync(off.data(), X.off.get(), (X.rows + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        // rows are ordered by GLOBAL popularity; a shard's own lengths follow it only on average, hence windows of 1024 rows
+        const double thr = (double)env_int("SVDLAS2_SPLIT_PER_PIECE", 6) * nslabs16;
+        u64 H = 0;
+        constexpr u64 win = 1024;
+        while (H + win <= X.rows && (double)(off[H + win] - off[H]) >= thr * win) H += win;
+        const u64 nnz_heavy = off[H], nnz_light = X.nnz - nnz_heavy;
+        if (H > 0 && H < X.rows && nnz_heavy >= kSlabMinNnz && nnz_light >= (u64)8 * kNumSMs * kSpmvTile && nslabs16 >= 2) {
+            const CsrView heavy{H, X.cols, nnz_heavy, X.off.get(), X.idx.get(), X.val.get()};
+            build_range(heavy, X.chk, 0, false, true, s, st);
+            DevBuf<u32> off2(X.rows - H + 1);
+            k_rebase_offsets<<<grid_for(X.rows - H + 1, 256), 256, 0, s>>>(X.off, (u32)H, (u32)(X.rows - H), off2);
+            LAS2_LAUNCH_CHECK();
+            const CsrView light{X.rows - H, X.cols, nnz_light, off2.get(), X.idx.get() + nnz_heavy, X.val.get() + nnz_heavy};
+            build_range(light, X.chk2, 0, false, false, s, st);
+            X.chk2.row0 = H;
+            LAS2_CUDA(cudaStreamSynchronize(s));
+            return;
+        }
+    }
+    build_range(whole, X.chk, X.hot_entries, slab_candidate, slab_mode == '1', s, st);
 }
 
-void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
-    const ChunkStream &K = A.chk;
+namespace {
+
+void run_stream(const DeviceCsr &A, const ChunkStream &K, const double *x, double *y, cudaStream_t s, u64 *launches) {
     u32 hot = 0;
-    if (K.slabs) {
+    if (K.slabs && K.slab_local) {
         hot = kSlabWidth;
-    } else {
-        hot = A.tune.hot_entries >= 0 ? (u32)A.tune.hot_entries : std::min<u32>(A.hot_entries, kChunkHotDefault);
+    } else if (!K.slabs) {
+        hot = A.tune.hot_entries >= 0 ? (u32)A.tune.hot_entries : std::min<u32>(K.hot_entries, kChunkHotDefault);
         hot = std::min<u32>(hot, kChunkHotMax);
         hot = (u32)std::min<u64>(hot, K.cols);
     }
@@ -983,8 +1047,8 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
     const u32 grid = std::min<u32>(kNumSMs, cdiv(K.num_chunks, warps));
     const u32 *rowmap = (!K.slabs && K.has_empty_rows) ? K.rowmap.get() : nullptr;
     double *out = K.slabs ? K.part.get() : y;
-    const int mode = K.slabs ? 2 : (hot > 0 ? 1 : 0);
-    if (mode != 2 && K.has_empty_rows) LAS2_CUDA(cudaMemsetAsync(y, 0, K.rows * sizeof(double), s));
+    const int mode = (K.slabs && K.slab_local) ? 2 : (hot > 0 ? 1 : 0);
+    if (!K.slabs && K.has_empty_rows) LAS2_CUDA(cudaMemsetAsync(y, 0, K.rows * sizeof(double), s));
 #define LAS2_CHUNK_LAUNCH(MODE, WARPS, STAGES, SLOT)                                                                   \
     do {                                                                                                               \
         configure((const void *)k_spmv_chunk<MODE, WARPS, STAGES>, g_chunk_carve[dev_slot][SLOT]);                               \
@@ -999,7 +1063,7 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
     launch_pdl(pdl, k_chunk_fixup, dim3(cdiv(K.num_chunks, 256)), dim3(256), 0, s, (const u32 *)K.fix_row, (const u32 *)K.fix_first,
                (const double *)K.carry, (const double *)K.head, out, K.num_chunks);
     if (launches) *launches += 2;
-    if (mode == 2) {
+    if (K.slabs) {
         launch_pdl(pdl, k_slab_reduce, dim3(cdiv(K.rows, 32)), dim3(kReduceWarps * 32), 0, s, (const u32 *)K.piece_id,
                    (const double *)K.part, (u64)K.rows, K.nslabs, y);
         if (launches) *launches += 1;
@@ -1007,9 +1071,15 @@ void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, 
     LAS2_LAUNCH_CHECK();
 }
 
+} // namespace
+
+void spmv_chunk(const DeviceCsr &A, const double *x, double *y, cudaStream_t s, u64 *launches) {
+    run_stream(A, A.chk, x, y + A.chk.row0, s, launches);
+    if (A.chk2.active) run_stream(A, A.chk2, x, y + A.chk2.row0, s, launches);
+}
 
 // ---- host side of the 4-RHS product --------------------------------------------------------------------------------
-bool spmm4_supported(const DeviceCsr &A) { return A.chk.active && !A.chk.slabs; }
+bool spmm4_supported(const DeviceCsr &A) { return A.chk.active && !A.chk.slabs && !A.chk2.active; }
 
 void Spmm4Work::ensure(const DeviceCsr &A) {
     const size_t nc = A.chk.num_chunks;

@@ -8,6 +8,10 @@
 #include "device_csr.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
+
+#include "comm.hpp"
 #include <vector>
 
 namespace las2 {
@@ -448,8 +452,125 @@ void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st); // chunk
 // its index range run the tile kernels on the natural CSR arrays)
 static void build_streams(DeviceCsr &X, cudaStream_t s, UploadStats &st) { build_chunk_stream(X, s, st); }
 
-void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, const u64 *indices, const double *values,
-                             cudaStream_t s, DeviceCsr &X, DeviceCsr &XT, UploadStats &st) {
+// ------------------------------------------------------------------------------------------------ relabelling
+namespace {
+
+__global__ void k_row_lengths(const u32 *__restrict__ off, u32 rows, double *__restrict__ len) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (; r < rows; r += stride) len[r] = (double)(off[r + 1] - off[r]);
+}
+// key = ~length (ascending key = descending length), payload = the row's old id, dummy value
+__global__ void k_length_keys(const double *__restrict__ len, u32 rows, u32 *__restrict__ key, u32 *__restrict__ id,
+                              double *__restrict__ dummy) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (; r < rows; r += stride) {
+        const double l = len[r];
+        key[r] = 0xffffffffu - (u32)(l > 4294967295.0 ? 4294967295.0 : l);
+        id[r] = r;
+        dummy[r] = 0.0;
+    }
+}
+__global__ void k_invert_perm(const u32 *__restrict__ new2old, u32 n, u32 *__restrict__ old2new) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (; i < n; i += stride) old2new[new2old[i]] = i;
+}
+// lengths of the rows in their new order (ne[rows] = 0 so that the scan leaves the total there)
+__global__ void k_permuted_lengths(const u32 *__restrict__ off, const u32 *__restrict__ new2old, u32 rows, u32 *__restrict__ out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (; i <= rows; i += stride) out[i] = i < rows ? off[new2old[i] + 1] - off[new2old[i]] : 0u;
+}
+// entries of new row i = entries of old row new2old[i], in their order
+__global__ void k_gather_rows(const u32 *__restrict__ off_old, const u32 *__restrict__ idx_old, const double *__restrict__ val_old,
+                              const u32 *__restrict__ off_new, const u32 *__restrict__ rowid_new, const u32 *__restrict__ new2old,
+                              u64 nnz, u32 *__restrict__ idx_new, double *__restrict__ val_new) {
+    u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; k < nnz; k += stride) {
+        const u32 i = rowid_new[k];
+        const u64 src = (u64)off_old[new2old[i]] + (k - off_new[i]);
+        idx_new[k] = idx_old[src];
+        val_new[k] = val_old[src];
+    }
+}
+
+bool relabel_wanted(const DeviceCsr &P) {
+    const char *e = std::getenv("SVDLAS2_RELABEL");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return P.nnz > 0 && P.rows > 1;
+    // worth it where the chunk-stream kernels run and the gathered vector is longer than a shared-memory prefix
+    return P.nnz >= (u64)8 * kNumSMs * kSpmvTile && P.rows > 2 * kHotPrefix;
+}
+
+} // namespace
+
+// P = B' (rows = the N side).  Re-numbers its rows in descending order of GLOBAL length (stable), rebuilds P in that order and
+// PT = B as its transpose (columns ascending in the new ids).  Deterministic; identical on every rank of a sharded run
+// (the lengths are summed over the ranks first).
+static void relabel_rows(DeviceCsr &P, DeviceCsr &PT, Relabel &R, Comm *comm, cudaStream_t s, UploadStats &st) {
+    const u32 rows = (u32)P.rows;
+    const unsigned g = std::max(1u, std::min<unsigned>(cdiv(rows, 256), kNumSMs * 8));
+    DevBuf<double> len(rows);
+    k_row_lengths<<<g, 256, 0, s>>>(P.off, rows, len);
+    LAS2_LAUNCH_CHECK();
+    if (comm) comm->allreduce_sum(len.get(), rows, s); // exact: integers far below 2^53
+    DevBuf<u32> key(rows), id(rows);
+    DevBuf<double> dummy(rows);
+    k_length_keys<<<g, 256, 0, s>>>(len, rows, key, id, dummy);
+    LAS2_LAUNCH_CHECK();
+    st.launches += 2;
+    SortBufs sb;
+    const int w = radix_sort(key, id, dummy, rows, 32, sb, s, st);
+    R.new2old = std::move(sb.pay[w]);
+    R.old2new.alloc(rows);
+    k_invert_perm<<<g, 256, 0, s>>>(R.new2old, rows, R.old2new);
+    LAS2_LAUNCH_CHECK();
+    R.h_new2old.resize(rows);
+    LAS2_CUDA(cudaMemcpyAsync(R.h_new2old.data(), R.new2old.get(), rows * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    // P in the new row order
+    DeviceCsr Pn;
+    Pn.rows = P.rows; Pn.cols = P.cols; Pn.nnz = P.nnz; Pn.padded_nnz = P.padded_nnz; Pn.tune = P.tune;
+    Pn.off.alloc(P.rows + 1);
+    k_permuted_lengths<<<g, 256, 0, s>>>(P.off, R.new2old, rows, Pn.off);
+    LAS2_LAUNCH_CHECK();
+    exclusive_scan(Pn.off, (u64)rows + 1, s, st);
+    Pn.idx.alloc(Pn.padded_nnz); Pn.val.alloc(Pn.padded_nnz);
+    if (P.nnz) {
+        DevBuf<u32> rowid(P.nnz);
+        expand_row_ids(Pn.off, rows, P.nnz, rowid, s, st);
+        unsigned gg = cdiv(P.nnz, 256 * 4);
+        if (gg > (unsigned)kNumSMs * 32) gg = kNumSMs * 32;
+        k_gather_rows<<<gg, 256, 0, s>>>(P.off, P.idx, P.val, Pn.off, rowid, R.new2old, P.nnz, Pn.idx, Pn.val);
+        LAS2_LAUNCH_CHECK();
+        st.launches++;
+        LAS2_CUDA(cudaStreamSynchronize(s));
+    }
+    finish_csr(Pn, s, st);
+    Pn.rows_sorted_desc = true;
+    P = std::move(Pn);
+    // PT = transpose of the re-ordered P: its column indices are the new ids, ascending inside every row
+    const SpmvTuning keep = PT.tune;
+    PT = DeviceCsr();
+    transpose_csr(P, PT, s, st);
+    PT.tune = keep;
+    LAS2_CUDA(cudaStreamSynchronize(s));
+    R.active = true;
+}
+
+// B / B' are complete in natural CSR form: relabel the N side where it pays, then build the SpMV streams
+static void finalize_operator(DeviceCsr &B, DeviceCsr &BT, Relabel &R, Comm *comm, cudaStream_t s, UploadStats &st) {
+    R = Relabel();
+    if (relabel_wanted(BT)) relabel_rows(BT, B, R, comm, s, st);
+    build_streams(B, s, st);
+    build_streams(BT, s, st);
+}
+
+// host CSR arrays -> X (rows x cols) and XT in natural device CSR form (no streams yet)
+static void upload_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, const u64 *indices, const double *values,
+                       cudaStream_t s, DeviceCsr &X, DeviceCsr &XT, UploadStats &st) {
     if (nnz >= ((u64)1 << 32) - 2 * kSpmvTile || rows >= ((u64)1 << 32) - 1 || cols >= ((u64)1 << 32) - 1)
         throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "matrix too large for 32-bit device indices (nnz, rows, cols must be < 2^32)");
     if (!offsets || (nnz && (!indices || !values))) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "null input array");
@@ -474,18 +595,23 @@ void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, co
     stage.release();
     finish_csr(X, s, st);
     transpose_csr(X, XT, s, st);
-    build_streams(X, s, st);
-    build_streams(XT, s, st);
 }
 
-void build_operator(const HostSparse &A, bool transposed, cudaStream_t s, DeviceCsr &B, DeviceCsr &BT, UploadStats &st) {
+void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, const u64 *indices, const double *values,
+                             cudaStream_t s, DeviceCsr &X, DeviceCsr &XT, UploadStats &st, Relabel &relabel, Comm *comm) {
+    upload_csr(rows, cols, nnz, offsets, indices, values, s, X, XT, st);
+    finalize_operator(X, XT, relabel, comm, s, st);
+}
+
+void build_operator(const HostSparse &A, bool transposed, cudaStream_t s, DeviceCsr &B, DeviceCsr &BT, UploadStats &st,
+                    Relabel &relabel) {
     DeviceCsr X, XT; // X = the matrix whose CSR the input arrays spell out; XT its transpose
     bool x_is_a = true;
     if (A.fmt == SVDLAS2_FMT_CSR) {
-        build_operator_from_csr(A.nrows, A.ncols, A.nnz, A.a, A.b, A.val, s, X, XT, st);
+        upload_csr(A.nrows, A.ncols, A.nnz, A.a, A.b, A.val, s, X, XT, st);
     } else if (A.fmt == SVDLAS2_FMT_CSC) {
         // CSC(A) arrays are CSR(A')
-        build_operator_from_csr(A.ncols, A.nrows, A.nnz, A.a, A.b, A.val, s, X, XT, st);
+        upload_csr(A.ncols, A.nrows, A.nnz, A.a, A.b, A.val, s, X, XT, st);
         x_is_a = false;
     } else if (A.fmt == SVDLAS2_FMT_COO) {
         if (A.nnz >= ((u64)1 << 32) - 2 * kSpmvTile || A.nrows >= ((u64)1 << 32) - 1 || A.ncols >= ((u64)1 << 32) - 1)
@@ -527,8 +653,6 @@ void build_operator(const HostSparse &A, bool transposed, cudaStream_t s, Device
         }
         finish_csr(X, s, st);
         transpose_csr(X, XT, s, st);
-        build_streams(X, s, st);
-        build_streams(XT, s, st);
     } else {
         throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "unknown sparse format");
     }
@@ -536,6 +660,7 @@ void build_operator(const HostSparse &A, bool transposed, cudaStream_t s, Device
     bool b_is_x = (x_is_a != transposed);
     if (b_is_x) { B = std::move(X); BT = std::move(XT); }
     else        { B = std::move(XT); BT = std::move(X); }
+    finalize_operator(B, BT, relabel, nullptr, s, st);
     LAS2_CUDA(cudaStreamSynchronize(s));
 }
 

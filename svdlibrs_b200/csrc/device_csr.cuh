@@ -5,6 +5,8 @@
 // for both B and B' (north star "Input upload"), so neither half of svd_opb (:829-837) needs atomics.
 #pragma once
 
+#include <vector>
+
 #include "util.cuh"
 
 namespace las2 {
@@ -33,6 +35,14 @@ constexpr u32 kSlabWidth = 16384;
 struct ChunkStream {
     bool active = false;
     bool slabs = false;
+    // slab flavours: LOCAL (width kSlabWidth, slab-local column indices, every gather from the slab's slice of x in shared
+    // memory) or WIDE (any width, global column indices, gathers through L1: the stream is merely ORDERED by slabs so that all
+    // CTAs gather from the same few MB of x at the same time -- an L2 / TLB blocking for gathered vectors far larger than L2's
+    // useful share, e.g. the 80 MB of t at cfg 4)
+    bool slab_local = false;
+    u32 slab_width = 0;
+    u64 row0 = 0;            // first row of y this stream produces (a matrix may be split into row ranges with different modes)
+    u32 hot_entries = 0;     // plain mode: size of the shared-memory prefix of x worth keeping (0: none)
     u64 rows = 0, cols = 0;
     u32 num_chunks = 0;
     u32 nonempty_rows = 0;   // plain: rows with entries; slab mode: non-empty (slab, row) pieces
@@ -66,7 +76,10 @@ struct SpmvTuning {
 struct DeviceCsr {
     u64 rows = 0, cols = 0, nnz = 0;
     SpmvTuning tune;
-    ChunkStream chk;
+    ChunkStream chk;  // rows [0, chk2.row0) -- or all rows when chk2 is not active
+    ChunkStream chk2; // optional second row range (the light rows of a frequency-ordered B')
+    // set by the upload-time relabelling for the matrix whose ROWS were put in descending order of (global) row length
+    bool rows_sorted_desc = false;
     DevBuf<u32> off;    // rows + 1 row offsets
     DevBuf<u32> idx;    // padded_nnz column indices (padding: index 0)
     DevBuf<double> val; // padded_nnz values        (padding: 0.0)
@@ -98,14 +111,29 @@ struct UploadStats {
     u64 launches = 0;
 };
 
+// Upload-time relabelling of the N side (the columns of B = the rows of B'), SURVEY 8(a) svd_opa: ids are re-assigned in
+// descending order of column popularity (stable), so that
+//   * the popular entries of the gathered vector x form a PREFIX whatever order the caller's matrix uses (the shared-memory
+//     prefix of k_spmv_chunk then serves half of the gathers of an LSA-shaped matrix), and
+//   * the rows of B' come out sorted by length, so that its heavy rows can run in slab mode and its light rows apart.
+// The Lanczos recurrence runs on P B'B P' (same mathematics, vectors in the new order); the start vector is permuted on the
+// way in and the N-side singular vectors on the way out, so callers never see the new ids.
+struct Relabel {
+    bool active = false;
+    DevBuf<u32> new2old, old2new;   // device copies (N entries each)
+    std::vector<u32> h_new2old;     // host copy (start vector, test hooks)
+};
+
+class Comm;
+
 // Builds CSR(B) and CSR(B') on the current device.  `transposed` is the orientation decision of
 // src/lib.rs:606 (B = A' when true).  Throws Error(SVDLAS2_ERR_INVALID_ARGUMENT) on malformed input.
 void build_operator(const HostSparse &A, bool transposed, cudaStream_t stream, DeviceCsr &B, DeviceCsr &BT,
-                    UploadStats &stats);
+                    UploadStats &stats, Relabel &relabel);
 
 // Builds the pair from a CSR row shard that is already oriented (multi-GPU path).
 void build_operator_from_csr(u64 rows, u64 cols, u64 nnz, const u64 *offsets, const u64 *indices,
                              const double *values, cudaStream_t stream, DeviceCsr &B, DeviceCsr &BT,
-                             UploadStats &stats);
+                             UploadStats &stats, Relabel &relabel, Comm *comm);
 
 } // namespace las2

@@ -34,6 +34,7 @@ namespace las2 {
 // vecops.cu
 void vec_sigma_scale(double *u, u64 m, const PartialSlot &t, double *sigma_out, cudaStream_t s);
 void vec_sumsq_any(const double *a, u64 n, PartialSlot &out, cudaStream_t s);
+void unpermute_rows(const double *V, u64 ld, u64 n, u32 d, const u32 *old2new, double *out, cudaStream_t s);
 
 namespace {
 
@@ -172,7 +173,14 @@ struct Solver {
         {
             std::vector<double> h(ld, 0.0);
             ChaCha12Stream g(seed); // rebuilt from the same seed on every call, :1109-1114
-            for (u64 i = 0; i < N; i++) h[i] = g.next_unit_pm1();
+            if (op.relabel.active) { // the same vector, element c of the caller's numbering at its new position
+                std::vector<double> ho(N);
+                for (u64 i = 0; i < N; i++) ho[i] = g.next_unit_pm1();
+                const std::vector<u32> &n2o = op.relabel.h_new2old;
+                for (u64 i = 0; i < N; i++) h[i] = ho[n2o[i]];
+            } else {
+                for (u64 i = 0; i < N; i++) h[i] = g.next_unit_pm1();
+            }
             LAS2_CUDA(cudaMemcpyAsync(xs.get(), h.data(), ld * sizeof(double), cudaMemcpyHostToDevice, s));
             LAS2_CUDA(cudaStreamSynchronize(s));
             prof.h2d_bytes += ld * sizeof(double);
@@ -485,9 +493,18 @@ struct Solver {
         struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } evdel{ev};
         LAS2_CUDA(cudaEventRecord(ev, s));
         LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
-        if (ncols)
+        DevBuf<double> Vout; // the N-side vectors in the caller's numbering (relabelled operators only)
+        if (ncols && op.relabel.active) {
+            Vout.alloc((size_t)d * N);
+            unpermute_rows(V.get(), ld, N, (u32)d, op.relabel.old2new.get(), Vout.get(), s);
+            prof.n_kernel_launches += 1;
+            LAS2_CUDA(cudaEventRecord(ev, s));
+            LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+            LAS2_CUDA(cudaMemcpyAsync(hV, Vout.get(), d * N * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
+        } else if (ncols) {
             LAS2_CUDA(cudaMemcpy2DAsync(hV, ncols * sizeof(double), V.get(), ld * sizeof(double), ncols * sizeof(double), d,
                                         cudaMemcpyDeviceToHost, copy_stream));
+        }
         DevBuf<double> U((size_t)d * mcols);
         DevBuf<double> S(d);
         DevBuf<double> nrm2(d); // |B_g v_i|^2 per triplet (summed over ranks when sharded)
@@ -575,7 +592,7 @@ struct Solver {
         prof.d2h_bytes += (d * ncols + d * mcols + d) * sizeof(double);
         prof.t_download = wall() - td0; // D2H time NOT hidden behind the sigma/U kernels
         const double tf0 = wall();
-        U.release(); V.release(); S.release(); nrm2.release();
+        U.release(); V.release(); S.release(); nrm2.release(); Vout.release();
         if (trace) fprintf(stderr, "[svdlas2] ritvec: device buffers released in %.3f s\n", wall() - tf0);
     }
 };

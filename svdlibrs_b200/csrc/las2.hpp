@@ -25,6 +25,7 @@ struct Operator {
     u64 N = 0;
     u64 row_begin = 0;
     DeviceCsr B, BT; // BT is N x M (local)
+    Relabel relabel;  // N-side ids re-assigned at upload (device_csr.cuh); vectors inside the solver are in the NEW order
     Comm *comm = nullptr; // borrowed; null on a single GPU
     // the exchange step of a sharded opb over NVLink peer memory, fused with the first update of the Lanczos step
     // (peer_ring.cuh); null on a single GPU, when peer memory cannot be mapped, or with SVDLAS2_RING=0 (then: ncclAllReduce)

@@ -131,7 +131,27 @@ __global__ void k_gather_scalars(GatherList g, double *__restrict__ out) {
     }
 }
 
+// out[i * n + c] = V[i * ld + old2new[c]]: the N-side singular vectors back in the caller's numbering (coalesced writes)
+__global__ void __launch_bounds__(kVecThreads)
+k_unpermute_rows(const double *__restrict__ V, u64 ld, u64 n, const u32 *__restrict__ old2new, double *__restrict__ out) {
+    const double *v = V + (u64)blockIdx.y * ld;
+    double *o = out + (u64)blockIdx.y * n;
+    u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; c < n; c += stride) o[c] = v[old2new[c]];
+}
+
 } // namespace
+
+void unpermute_rows(const double *V, u64 ld, u64 n, u32 d, const u32 *old2new, double *out, cudaStream_t s) {
+    if (d == 0 || n == 0) return;
+    const unsigned gx = (unsigned)std::max<u64>(1, std::min<u64>((n + kVecThreads * 4 - 1) / (kVecThreads * 4), 4 * kNumSMs));
+    for (u32 d0 = 0; d0 < d; d0 += 65535) {
+        const u32 nd = std::min<u32>(65535, d - d0);
+        k_unpermute_rows<<<dim3(gx, nd), kVecThreads, 0, s>>>(V + (u64)d0 * ld, ld, n, old2new, out + (u64)d0 * n);
+    }
+    LAS2_LAUNCH_CHECK();
+}
 
 unsigned vec_grid(u64 ld) {
     u64 n2 = ld / 2;

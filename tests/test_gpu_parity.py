@@ -479,3 +479,85 @@ def test_peer_ring_kernel_emulated_ranks(las2, G, two_shot, ctas):
             assert np.array_equal(out[g], want), (g, np.abs(out[g] - want).max())
         assert np.all(dots == dots[0])
         assert abs(dots[0] - want @ q) <= 1e-11 * np.linalg.norm(want) * np.linalg.norm(q)
+
+
+def _layout(las2, op):
+    import ctypes as C
+    from svdlibrs_b200 import _lib
+    L = _lib.lib()
+    L.svdlas2_test_operator_layout.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.svdlas2_test_operator_layout.restype = C.c_int
+    out = (C.c_double * 8)()
+    assert L.svdlas2_test_operator_layout(op._h, out) == 0
+    return dict(relabelled=bool(out[0]), hot_fraction=out[1], hot_entries=int(out[2]), mode_b=int(out[3]), mode_bt=int(out[4]),
+                mode_bt2=int(out[5]), split_row=int(out[6]), nslabs=int(out[7]))
+
+
+def test_input_order_independence(las2, oracle):
+    """The gather of svd_opa (reference src/lib.rs:2087-2091) has no precondition on the column order.  The upload relabels the N
+    side by popularity, so a matrix whose column ids are RANDOMLY PERMUTED gets the same device layout (same share of gathers
+    served from the shared-memory prefix) as the frequency-ordered one, and its solve matches the oracle run on that same
+    permuted matrix (vectors come back in the caller's numbering)."""
+    from svdlibrs_b200 import synthetic
+    A, _ = synthetic.make("cfg2", scale=0.25)                 # 250k x 25k, ~1.1e7 nnz: chunk streams + relabelling are on
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(A.shape[1])
+    Ap = A[:, perm].tocsr()
+    Ap.sort_indices()
+    lay = []
+    for M in (A, Ap):
+        with las2.Operator(M) as op:
+            lay.append(_layout(las2, op))
+            x = rng.standard_normal(M.shape[1])
+            y, y0 = op.opa(x), oracle.opa(M, x)
+            assert np.linalg.norm(y - y0) <= 1e-13 * np.linalg.norm(y0)
+            t = rng.standard_normal(M.shape[0])
+            z, z0 = op.opa(t, True), oracle.opa(M, t, True)
+            assert np.linalg.norm(z - z0) <= 1e-13 * np.linalg.norm(z0)
+            w, w0 = op.opb(x), oracle.opb(M, x)
+            assert np.linalg.norm(w - w0) <= 1e-13 * np.linalg.norm(w0)
+    assert lay[0]["relabelled"] and lay[1]["relabelled"]
+    assert lay[0]["hot_fraction"] == lay[1]["hot_fraction"] and lay[0]["hot_fraction"] > 0.4
+    assert lay[0]["hot_entries"] == lay[1]["hot_entries"] > 0
+    got, ref = las2.svd_dim_seed(Ap, 20, 12345), oracle.svd_dim_seed(Ap, 20, 12345)
+    assert_svd_parity(got, ref)
+
+
+@pytest.mark.parametrize("env", [dict(SVDLAS2_RELABEL="1", SVDLAS2_SPMV="chunk"),
+                                 dict(SVDLAS2_RELABEL="1", SVDLAS2_SPMV="chunk", SVDLAS2_WIDE_SLABS="1"),
+                                 dict(SVDLAS2_RELABEL="0", SVDLAS2_SPMV="chunk")])
+def test_relabelled_and_wide_slab_layouts_at_test_size(las2, oracle, env, monkeypatch):
+    """Relabelling and the wide-slab ordering forced on matrices far below their thresholds: solves match the oracle (incl. the
+    transposed path, where the N side is rows(A)), opa / opb match for both orientations."""
+    from svdlibrs_b200 import synthetic
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(9)
+    for name, scale, dims in (("cfg2", 0.02, 20), ("cfg3", 0.01, 12)):
+        A, _ = synthetic.make(name, scale=scale)
+        with las2.Operator(A) as op:
+            lay = _layout(las2, op)
+            assert lay["relabelled"] == (env["SVDLAS2_RELABEL"] == "1")
+            for transposed in (False, True):
+                x = rng.standard_normal(A.shape[0] if transposed else A.shape[1])
+                y, y0 = op.opa(x, transposed), oracle.opa(A, x, transposed)
+                assert np.linalg.norm(y - y0) <= 1e-13 * np.linalg.norm(y0)
+            got = op.solve(dims, random_seed=12345)
+        assert_svd_parity(got, oracle.svd_dim_seed(A, dims, 12345))
+
+
+def test_heavy_light_split_of_bt(las2, oracle, monkeypatch):
+    """A frequency-ordered B' is cut into heavy rows (slab-local stream) and light rows (their own stream); forced here at test
+    size by lowering the per-piece threshold.  Both streams together must reproduce B' t, and the solve the oracle's."""
+    from svdlibrs_b200 import synthetic
+    monkeypatch.setenv("SVDLAS2_RELABEL", "1")
+    A, _ = synthetic.make("cfg2", scale=0.6)                  # 600k x 60k, ~2.7e7 nnz: above the 20 M-nnz slab threshold
+    rng = np.random.default_rng(13)
+    with las2.Operator(A) as op:
+        lay = _layout(las2, op)
+        assert lay["relabelled"] and lay["mode_bt"] == 2 and lay["mode_bt2"] in (0, 3) and lay["split_row"] > 0, lay
+        t = rng.standard_normal(A.shape[0])
+        z, z0 = op.opa(t, True), oracle.opa(A, t, True)
+        assert np.linalg.norm(z - z0) <= 1e-13 * np.linalg.norm(z0)
+        got = op.solve(10, random_seed=12345)
+    assert_svd_parity(got, oracle.svd_dim_seed(A, 10, 12345))
