@@ -38,6 +38,12 @@ SVDLAS2_API int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, in
  * tail computes it.  Returns SVDLAS2_ERR_INVALID_ARGUMENT when the operator's B is not on the chunk stream. */
 SVDLAS2_API int svdlas2_test_spmm4(svdlas2_operator *op, uint32_t nv, const double *X, double *Y, double *sumsq);
 
+/* GPU tuning / test hook for the Ritz back-transform V = Q C of ritvec (src/lib.rs:1807-1817): Q is n x js (pseudo-random), C is
+ * js x d; both kernels run `reps` times: ms[0] = FMA-pipe register tile (k_ritz_contract), ms[1] = DMMA tile kernel
+ * (k_ritz_contract_dmma); max_diff = largest |V_fma - V_dmma| relative to the largest |V|; max_err = largest deviation of the
+ * DMMA result from a host-computed double-double reference on a sample of entries, same scale. */
+SVDLAS2_API int svdlas2_test_time_ritz(uint64_t n, uint32_t js, uint32_t d, int reps, int device, double ms[2], double *max_diff,
+                                       double *max_err);
 /* How the upload laid the operator out: out[0] = 1 when the N side was relabelled by popularity, out[1] = share of B's column
  * indices inside the shared-memory prefix (hot_fraction), out[2] = size of that prefix, out[3] / out[4] = mode of B's / B''s
  * first stream and out[5] of B''s second one (-1 none, 0 plain, 1 plain + hot prefix, 2 slab-local, 3 wide slabs),

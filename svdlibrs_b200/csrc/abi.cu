@@ -1,5 +1,6 @@
 // abi.cu -- the extern "C" boundary declared in include/svdlas2.h.  Exceptions never cross it: every entry
 // point maps las2::Error (and anything else) to a status code and a thread-local message.
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -326,6 +327,65 @@ int svdlas2_test_time_panel(uint64_t n, uint32_t ncols, int reps, int device, do
         cudaStreamDestroy(s);
         if (ms_dots) *ms_dots = td / reps;
         if (ms_update) *ms_update = tu / reps;
+    });
+}
+
+int svdlas2_test_time_ritz(uint64_t n, uint32_t js, uint32_t d, int reps, int device, double ms[2], double *max_diff, double *max_err) {
+    if (n == 0 || js == 0 || d == 0 || reps < 1 || !ms) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        if (device >= 0) LAS2_CUDA(cudaSetDevice(device));
+        const u64 ld = (n + 31) / 32 * 32;
+        cudaStream_t s;
+        LAS2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        struct SDel { cudaStream_t s; ~SDel() { cudaStreamDestroy(s); } } sdel{s};
+        // pseudo-random entries in [-1, 1): cheap on the host for C, hashed on the host for a strip of Q and replicated
+        std::vector<double> hC((size_t)js * d), hQ((size_t)ld * js, 0.0);
+        u64 st = 0x243F6A8885A308D3ull;
+        auto rnd = [&] { st = st * 6364136223846793005ull + 1442695040888963407ull; return (double)(st >> 11) * (2.0 / 9007199254740992.0) - 1.0; };
+        for (auto &v : hC) v = rnd();
+        for (u32 k = 0; k < js; k++)
+            for (u64 i = 0; i < n; i++) hQ[(size_t)k * ld + i] = rnd();
+        DevBuf<double> Q((size_t)ld * js), C((size_t)js * d), V0((size_t)ld * d), V1((size_t)ld * d);
+        LAS2_CUDA(cudaMemcpyAsync(Q.get(), hQ.data(), hQ.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        LAS2_CUDA(cudaMemcpyAsync(C.get(), hC.data(), hC.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        cudaEvent_t e0, e1;
+        LAS2_CUDA(cudaEventCreate(&e0)); LAS2_CUDA(cudaEventCreate(&e1));
+        for (int variant = 0; variant < 2; variant++) {
+            g_ritz_variant = variant;
+            double *V = variant ? V1.get() : V0.get();
+            LAS2_CUDA(cudaMemsetAsync(V, 0xff, (size_t)ld * d * sizeof(double), s));
+            ritz_contract(Q.get(), ld, n, js, C.get(), d, V, s, nullptr); // warm-up
+            LAS2_CUDA(cudaEventRecord(e0, s));
+            for (int r = 0; r < reps; r++) ritz_contract(Q.get(), ld, n, js, C.get(), d, V, s, nullptr);
+            LAS2_CUDA(cudaEventRecord(e1, s));
+            LAS2_CUDA(cudaStreamSynchronize(s));
+            float t = 0.f;
+            LAS2_CUDA(cudaEventElapsedTime(&t, e0, e1));
+            ms[variant] = t / reps;
+        }
+        g_ritz_variant = -1;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        std::vector<double> h0((size_t)ld * d), h1((size_t)ld * d);
+        LAS2_CUDA(cudaMemcpy(h0.data(), V0.get(), h0.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        LAS2_CUDA(cudaMemcpy(h1.data(), V1.get(), h1.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        double vmax = 0.0, dmax = 0.0, emax = 0.0;
+        for (u32 c = 0; c < d; c++)
+            for (u64 i = 0; i < n; i++) {
+                const double a = h0[(size_t)c * ld + i], b = h1[(size_t)c * ld + i];
+                vmax = std::max(vmax, std::fabs(a));
+                dmax = std::max(dmax, std::fabs(a - b));
+            }
+        // reference in long double on a sample of entries
+        const u64 stride_i = std::max<u64>(1, n / 97);
+        const u32 stride_c = std::max<u32>(1, d / 13);
+        for (u32 c = 0; c < d; c += stride_c)
+            for (u64 i = 0; i < n; i += stride_i) {
+                long double acc = 0.0L;
+                for (u32 k = 0; k < js; k++) acc += (long double)hQ[(size_t)k * ld + i] * (long double)hC[(size_t)k * d + c];
+                emax = std::max(emax, (double)fabsl(acc - (long double)h1[(size_t)c * ld + i]));
+            }
+        if (max_diff) *max_diff = vmax > 0 ? dmax / vmax : dmax;
+        if (max_err) *max_err = vmax > 0 ? emax / vmax : emax;
     });
 }
 

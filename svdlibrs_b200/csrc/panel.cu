@@ -224,6 +224,103 @@ k_ritz_contract(const double *__restrict__ Q, u64 ld, u32 js, const double *__re
     }
 }
 
+// ---- Ritz contraction on the FP64 tensor path (DMMA m8n8k4) ----------------------------------------------
+// V[rows, c0 .. c0+64) = Q[rows, 0 .. js) . C[0 .. js, c0 .. c0+64) for a block of 128 rows: 8 warps, each a 32 x 32 tile of
+// 4 x 4 mma tiles (32 accumulators per thread); the 128 x 16 slice of Q and the 16 x 64 slice of C of every k-step are staged
+// in shared memory (double-buffered, cp.async), so a row block of Q is read d / 64 times instead of d / 8 (k_ritz_contract re-reads
+// the panel 125 times at d = 1000 and is bandwidth-bound on exactly that, profiles/r2_ritz_ncu_summary.md).  Row padding of 4
+// doubles makes both fragment reads conflict-free.  The accumulation order is fixed (k ascending, 4 products per instruction).
+constexpr int kDmTM = 128, kDmTN = 64, kDmTK = 16, kDmThreads = 256;
+constexpr int kDmLdA = kDmTM + 4, kDmLdB = kDmTN + 4;
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool pred) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = pred ? 16 : 0; // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kDmThreads, 2)
+k_ritz_contract_dmma(const double *__restrict__ Q, u64 ld, u32 js, const double *__restrict__ C, u32 d, double *__restrict__ V,
+                     u64 row_lo, u64 row_hi) {
+    extern __shared__ __align__(16) double dm_smem[];
+    double (*As)[kDmTK][kDmLdA] = reinterpret_cast<double (*)[kDmTK][kDmLdA]>(dm_smem);
+    double (*Bs)[kDmTK][kDmLdB] = reinterpret_cast<double (*)[kDmTK][kDmLdB]>(dm_smem + 2 * kDmTK * kDmLdA);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;       // warp tile: rows wm*32, cols wn*32
+    const int fr = lane >> 2, fk = lane & 3;        // fragment coordinates
+    const u64 row0 = row_lo + (u64)blockIdx.x * kDmTM;
+    const u32 c0 = blockIdx.y * kDmTN;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto load_tiles = [&](int buf, u32 k0) {
+        // Q slice: 16 k x 128 rows = 1024 x 16 B, four per thread (rows are contiguous in the column-major panel)
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int e = tid + t * kDmThreads;       // 0 .. 1023
+            const int k = e >> 6, r2 = (e & 63) * 2;  // row pair
+            const u64 row = row0 + r2;
+            const bool ok = (k0 + k < js) && (row < row_hi);
+            const double *src = ok ? Q + (u64)(k0 + k) * ld + row : Q;
+            cp_async16(&As[buf][k][r2], src, ok);
+        }
+        // C slice: 16 k x 64 columns (row-major js x d, any d: plain loads with guards)
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int e = tid + t * kDmThreads;       // 0 .. 1023
+            const int k = e >> 6, c = e & 63;
+            const bool ok = (k0 + k < js) && (c0 + c < d);
+            Bs[buf][k][c] = ok ? C[(u64)(k0 + k) * d + c0 + c] : 0.0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const u32 nk = (js + kDmTK - 1) / kDmTK;
+    load_tiles(0, 0);
+    for (u32 it = 0; it < nk; it++) {
+        const int buf = it & 1;
+        if (it + 1 < nk) {
+            load_tiles(buf ^ 1, (it + 1) * kDmTK);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kDmTK; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[buf][kk + fk][wm * 32 + i * 8 + fr];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[buf][kk + fk][wn * 32 + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+    // C fragment: row = lane / 4, columns (lane % 4) * 2 and + 1
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u64 row = row0 + wm * 32 + i * 8 + fr;
+        if (row >= row_hi) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const u32 col = c0 + wn * 32 + j * 8 + fk * 2;
+            if (col < d) V[(u64)col * ld + row] = acc[i][j][0];
+            if (col + 1 < d) V[(u64)(col + 1) * ld + row] = acc[i][j][1];
+        }
+    }
+}
+
 } // namespace
 
 void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, double *b, PanelWork &work,
@@ -322,6 +419,8 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
     LAS2_LAUNCH_CHECK();
 }
 
+int g_ritz_variant = -1; // test / tuning hook (svdlas2_test_time_ritz): -1 auto, 0 FMA pipe, 1 DMMA
+
 void ritz_contract(const double *Q, u64 ld, u64 n, u32 js, const double *C, u32 d, double *V, cudaStream_t s,
                    u64 *launches, Comm *comm, bool *sharded) {
     (void)n;
@@ -343,8 +442,25 @@ void ritz_contract(const double *Q, u64 ld, u64 n, u32 js, const double *C, u32 
         i1 = offs[comm->rank() + 1] / 2;
     }
     if (i1 > i0) {
-        dim3 grid(cdiv(i1 - i0, kRitzThreads), cdiv(d, kRitzCols));
-        k_ritz_contract<<<grid, kRitzThreads, 0, s>>>(Q, ld, js, C, d, V, i0, i1);
+        // SVDLAS2_RITZ: "dmma" (default for contractions whose panel re-reads would dominate) or "fma" (the 2 x 8 register
+        // tile on the FMA pipe); both are bit-reproducible, each element is formed by one thread / one warp
+        static const int want = [] { const char *e = std::getenv("SVDLAS2_RITZ"); return !e ? -1 : (e[0] == 'f' ? 0 : 1); }();
+        const int variant = g_ritz_variant >= 0 ? g_ritz_variant : want;
+        const bool dmma = variant == 1 || (variant < 0 && d >= 16 && js >= 16);
+        if (dmma) {
+            constexpr size_t smem = (size_t)2 * kDmTK * (kDmLdA + kDmLdB) * sizeof(double); // 51,200 B
+            static bool configured[kMaxDevicesTracked];
+            bool &done = configured[current_device_slot()];
+            if (!done) {
+                LAS2_CUDA(cudaFuncSetAttribute(k_ritz_contract_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                done = true;
+            }
+            dim3 grid(cdiv(2 * (i1 - i0), kDmTM), cdiv(d, kDmTN));
+            k_ritz_contract_dmma<<<grid, kDmThreads, smem, s>>>(Q, ld, js, C, d, V, 2 * i0, 2 * i1);
+        } else {
+            dim3 grid(cdiv(i1 - i0, kRitzThreads), cdiv(d, kRitzCols));
+            k_ritz_contract<<<grid, kRitzThreads, 0, s>>>(Q, ld, js, C, d, V, i0, i1);
+        }
         LAS2_LAUNCH_CHECK();
         if (launches) *launches += 1;
     }

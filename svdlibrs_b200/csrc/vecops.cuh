@@ -81,5 +81,6 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
 // C is js x d row-major on the device; V is column-major with leading dimension ld (each Ritz vector contiguous).
 void ritz_contract(const double *Q, u64 ld, u64 n, u32 js, const double *C, u32 d, double *V, cudaStream_t s,
                    u64 *launches, Comm *comm = nullptr, bool *sharded = nullptr);
+extern int g_ritz_variant; // test / tuning hook: -1 auto (SVDLAS2_RITZ), 0 FMA pipe, 1 DMMA
 
 } // namespace las2

@@ -438,14 +438,13 @@ def test_spmm4_columns_equal_the_spmv(las2, monkeypatch):
     A2 = sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(lens.size, 6000))
     for A in (A1, A2):
         with las2.Operator(A) as op:
-            assert not op.transposed
             for nv in (4, 1, 3):
-                X = rng.standard_normal((nv, A.shape[1]))
-                Y = np.empty((nv, A.shape[0])); ss = np.empty(nv)
+                X = rng.standard_normal((nv, op.n))     # B is M x N (B = A, or A' on the transposed path)
+                Y = np.empty((nv, op.m)); ss = np.empty(nv)
                 rc = L.svdlas2_test_spmm4(op._h, nv, X.ctypes.data_as(f64p), Y.ctypes.data_as(f64p), ss.ctypes.data_as(f64p))
                 assert rc == 0, L.svdlas2_last_error()
                 for r in range(nv):
-                    y = op.opa(X[r])
+                    y = op.opa(X[r], op.transposed)     # B x
                     assert np.array_equal(Y[r], y), (nv, r, np.abs(Y[r] - y).max())
                     assert abs(ss[r] - y @ y) <= 1e-12 * (y @ y)
 
@@ -561,3 +560,19 @@ def test_heavy_light_split_of_bt(las2, oracle, monkeypatch):
         assert np.linalg.norm(z - z0) <= 1e-13 * np.linalg.norm(z0)
         got = op.solve(10, random_seed=12345)
     assert_svd_parity(got, oracle.svd_dim_seed(A, 10, 12345))
+
+
+@pytest.mark.parametrize("n,js,d", [(5000, 37, 9), (4096, 128, 64), (10007, 301, 130)])
+def test_ritz_contraction_variants_agree(las2, n, js, d):
+    """V = Q C of ritvec (reference src/lib.rs:1807-1817): the DMMA tile kernel against the FMA-pipe kernel and against a
+    long-double host reference, on ragged shapes (rows / js / d not multiples of the 128 x 16 x 64 tiles)."""
+    import ctypes as C
+    from svdlibrs_b200 import _lib
+    L = _lib.lib()
+    L.svdlas2_test_time_ritz.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.svdlas2_test_time_ritz.restype = C.c_int
+    ms, diff, err = (C.c_double * 2)(), C.c_double(), C.c_double()
+    rc = L.svdlas2_test_time_ritz(n, js, d, 1, -1, ms, C.byref(diff), C.byref(err))
+    assert rc == 0, L.svdlas2_last_error()
+    assert diff.value <= 1e-13 * js ** 0.5 and err.value <= 1e-13 * js ** 0.5, (diff.value, err.value)
