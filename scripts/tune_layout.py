@@ -26,6 +26,13 @@ print(f"generated {len(val)} nnz in {time.time() - t0:.1f} s", flush=True)
 import svdlibrs_b200 as las2
 m = (rows[1] - rows[0]) if rows else nrows
 A = las2.RawMatrix("csr", (m, ncols), indptr.astype(np.uint64), idx.view(np.uint64), val)
+
+
+def make_op():
+    # a shard is uploaded exactly as a rank of a sharded run uploads it (B = the shard's rows, N side = all columns)
+    if a.shard > 1:
+        return las2.ShardedOperator(A, nrows, rows[0], int(len(val)) * a.shard, None, False)
+    return las2.Operator(A)
 SETS = {
     "base": ({}, {}),
     "pp3": ({"SVDLAS2_SPLIT_PER_PIECE": "3"}, {}), "pp4": ({"SVDLAS2_SPLIT_PER_PIECE": "4"}, {}),
@@ -43,7 +50,7 @@ for name in a.sets.split(","):
     os.environ.update(env)
     try:
         t0 = time.time()
-        with las2.Operator(A) as op:
+        with make_op() as op:
             up = time.time() - t0
             for k, v in knobs.items():
                 op.set(k, v)

@@ -995,7 +995,7 @@ void build_chunk_stream(DeviceCsr &X, cudaStream_t s, UploadStats &st) {
         LAS2_CUDA(cudaMemcpyAsync(off.data(), X.off.get(), (X.rows + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s));
         LAS2_CUDA(cudaStreamSynchronize(s));
         // rows are ordered by GLOBAL popularity; a shard's own lengths follow it only on average, hence windows of 1024 rows
-        const double thr = (double)env_int("SVDLAS2_SPLIT_PER_PIECE", 6) * nslabs16;
+        const double thr = (double)env_int("SVDLAS2_SPLIT_PER_PIECE", 4) * nslabs16; // cfg 4: 3 / 4 / 6 / 8 / 12 -> B' 2.99 / 3.00 / 3.03 / 3.05 / 3.11 ms
         u64 H = 0;
         constexpr u64 win = 1024;
         while (H + win <= X.rows && (double)(off[H + win] - off[H]) >= thr * win) H += win;

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 
+#include "peer_ring.cuh"
 #include "util.cuh"
 
 namespace las2 {
@@ -83,16 +84,22 @@ Comm *Comm::create(int rank, int world, const uint8_t *id_bytes) {
     int rc = a.CommInitRank(&comm, world, id, rank);
     if (rc != 0) { delete c; check(rc, "ncclCommInitRank"); }
     c->nccl_comm_ = comm;
+    const char *ring_env = std::getenv("SVDLAS2_RING");
+    if (!(ring_env && ring_env[0] == '0')) {
+        try { c->small_ = PeerRing::create(c, 0); } catch (const Error &) { c->small_ = nullptr; } // collective, same verdict everywhere
+    }
     return c;
 }
 
 Comm::~Comm() {
+    delete small_;
     if (stage_) cudaFree(stage_);
     if (nccl_comm_) api().CommDestroy(nccl_comm_);
 }
 
 void Comm::allreduce_sum(double *buf, uint64_t n, cudaStream_t s) {
     if (world_ == 1) return;
+    if (small_ && n <= kRingSmallCap) { small_->allreduce_small(buf, n, s); return; }
     check(api().AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, nccl_comm_, s), "ncclAllReduce");
 }
 

@@ -9,6 +9,8 @@
 
 namespace las2 {
 
+struct PeerRing;
+
 class Comm {
   public:
     // id: SVDLAS2_COMM_ID_BYTES opaque bytes produced by unique_id() on rank 0 and broadcast by the caller
@@ -29,6 +31,9 @@ class Comm {
     Comm() = default;
     int rank_ = 0, world_ = 1;
     void *nccl_comm_ = nullptr;
+    // short sums (reorthogonalisation coefficients, squared norms, the shared seed) go through a peer-memory ring that adds
+    // in rank order (peer_ring.cuh) when peer memory is available: no floating-point result then depends on NCCL's choices
+    PeerRing *small_ = nullptr;
     void *stage_ = nullptr; // all-gather staging (world * largest range doubles)
     uint64_t stage_cap_ = 0;
 };

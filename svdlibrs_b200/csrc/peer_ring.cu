@@ -3,6 +3,7 @@
 // the push of the finished slice into every peer.
 #include "peer_ring.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -145,11 +146,11 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
-static void fill_args(const PeerRing &R, RingArgs &a, unsigned long long seq) {
+static void fill_args(const PeerRing &R, RingArgs &a, unsigned long long seq, bool small = false) {
     std::memset(&a, 0, sizeof a);
     for (int h = 0; h < R.G; h++) {
-        a.y[h] = reinterpret_cast<const double2 *>(R.y[seq & 1][h]);
-        a.r[h] = reinterpret_cast<double2 *>(R.r[h]);
+        a.y[h] = reinterpret_cast<const double2 *>(small ? R.ys[seq & 1][h] : R.y[seq & 1][h]);
+        a.r[h] = reinterpret_cast<double2 *>(small ? R.rs[h] : R.r[h]);
         a.parts[h] = R.parts[h];
         a.flags[h] = R.flags[h];
     }
@@ -164,12 +165,18 @@ static void layout(PeerRing &R, int h, void *base) {
     R.y[1][h] = reinterpret_cast<double *>(p + vec);
     R.r[h] = reinterpret_cast<double *>(p + 2 * vec);
     R.parts[h] = reinterpret_cast<double *>(p + 3 * vec);
-    R.flags[h] = reinterpret_cast<unsigned long long *>(p + 3 * vec + align_up((size_t)kRingMaxRanks * kRingCtas * sizeof(double), 256));
+    char *q = p + 3 * vec + align_up((size_t)kRingMaxRanks * kRingCtas * sizeof(double), 256);
+    R.flags[h] = reinterpret_cast<unsigned long long *>(q);
+    q += align_up(kFlagWords * sizeof(unsigned long long), 256);
+    const size_t sv = align_up(kRingSmallCap * sizeof(double), 256);
+    R.ys[0][h] = reinterpret_cast<double *>(q);
+    R.ys[1][h] = reinterpret_cast<double *>(q + sv);
+    R.rs[h] = reinterpret_cast<double *>(q + 2 * sv);
 }
 
 static size_t block_bytes(u64 cap) {
     return 3 * align_up(cap * sizeof(double), 256) + align_up((size_t)kRingMaxRanks * kRingCtas * sizeof(double), 256) +
-           align_up(kFlagWords * sizeof(unsigned long long), 256) + 256;
+           align_up(kFlagWords * sizeof(unsigned long long), 256) + 3 * align_up(kRingSmallCap * sizeof(double), 256) + 256;
 }
 
 PeerRing *PeerRing::create(Comm *comm, u64 n_doubles) {
@@ -239,6 +246,23 @@ void PeerRing::reduce(u64 ld, const double *qprev, double rnm, const double *q, 
         dot->parts = parts[g];
         dot->nparts = two_shot ? G * kRingCtas : kRingCtas;
     }
+}
+
+void PeerRing::allreduce_small(double *buf, u64 n, cudaStream_t s) {
+    if (n == 0) return;
+    if (n > kRingSmallCap) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "peer ring: small all-reduce beyond its capacity");
+    seq += 1;
+    calls += 1;
+    const u64 n_even = (n + 1) & ~(u64)1; // the kernel works on double2; the pad element is zero on every rank
+    double *mine = ys[seq & 1][g];
+    if (n_even != n) LAS2_CUDA(cudaMemsetAsync(mine + n, 0, sizeof(double), s));
+    LAS2_CUDA(cudaMemcpyAsync(mine, buf, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    RingArgs a;
+    fill_args(*this, a, seq, true);
+    const unsigned ctas = (unsigned)std::max<u64>(1, std::min<u64>(16, (n_even / 2 + kRingThreads - 1) / kRingThreads));
+    k_allreduce_epilogue<false, false><<<dim3(ctas, 1), kRingThreads, 0, s>>>(a, nullptr, n_even / 2, nullptr, 0.0, nullptr, 0);
+    LAS2_LAUNCH_CHECK();
+    LAS2_CUDA(cudaMemcpyAsync(buf, rs[g], n * sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 
 // ---- single-GPU emulation of G ranks (tests): one launch, blockIdx.y = rank, all CTAs co-resident ----------------------

@@ -23,6 +23,7 @@ class Comm;
 
 constexpr int kRingMaxRanks = 8;
 constexpr int kRingCtas = kNumSMs; // one CTA per SM; also the number of dot partials a rank contributes
+constexpr u64 kRingSmallCap = 16384; // doubles: the small channel (reorthogonalisation coefficients, squared norms, counts)
 
 struct PeerRing {
     int G = 1, g = 0;
@@ -32,6 +33,8 @@ struct PeerRing {
     double *y[2][kRingMaxRanks] = {};             // partial products, by call parity
     double *r[kRingMaxRanks] = {};                // the reduced vector (w0 of the reference) on every rank
     double *parts[kRingMaxRanks] = {};            // G * kRingCtas dot partials on every rank
+    double *ys[2][kRingMaxRanks] = {};            // small channel: inputs by call parity ...
+    double *rs[kRingMaxRanks] = {};               // ... and the result
     unsigned long long *flags[kRingMaxRanks] = {}; // 4 x kRingMaxRanks flag words on every rank
     unsigned long long seq = 0;                   // call number (same on every rank: the ranks run in lockstep)
     u64 two_shot_min_bytes = 2u << 20;
@@ -47,6 +50,9 @@ struct PeerRing {
     // r = sum_g y_g - rnm * qprev (qprev == nullptr: plain sum), dot partials of r . q (q == nullptr: none) into `dot`
     // (dot->parts then points into the ring's partial buffer).  ld2 = length in double2 units.
     void reduce(u64 ld, const double *qprev, double rnm, const double *q, PartialSlot *dot, cudaStream_t s);
+    // in-place sum over the ranks of a SHORT device vector (n <= kRingSmallCap), added in rank order like everything else:
+    // every floating-point reduction across ranks is then independent of NCCL's algorithm / protocol choices
+    void allreduce_small(double *buf, u64 n, cudaStream_t s);
 };
 
 void ring_quiesce(PeerRing &R, cudaStream_t s);
