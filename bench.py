@@ -484,6 +484,16 @@ def run_ours(args):
     # ---------------- roofline leg: the dominant kernel, timed live with CUDA events on the library's stream
     flush = 24 * W.local_nnz <= 4 * 126e6
     tm = op.time_opb(reps=20 if W.local_nnz < 3e8 else 10, flush_l2=flush)
+    exchange = None
+    if world > 1:
+        ring = bool(op.info("ring"))
+        exchange = {"kind": "peer-memory kernel over NVLink, fused with r -= rnm q and the alf partials (rank-ordered sum)" if ring
+                    else "ncclAllReduce + separate update kernel",
+                    "ring": ring, "two_shot": bool(op.info("ring_two_shot_calls") > 0),
+                    "nvlink_bytes_per_rank_per_opb": op.info("ring_bytes_per_call") if ring else None,
+                    "calls": int(op.info("ring_calls"))}
+    relabelled = bool(op.info("relabelled"))
+    hot_fraction = op.info("hot_fraction")
     barrier()
     clocks = sampler.stop(mark0, sampler.mark() + 1) if rank == 0 else None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -559,7 +569,8 @@ def run_ours(args):
                     "host_buffers": "pinned in place (cudaHostRegister)" if pinned else "pageable"},
             "time_to_svd_s": {"resident": t_dev / args.steps, "resident_wall": wall_resident / args.steps,
                               "e2e": t_e2e / e2e_steps, "first_upload": upload_first_s},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "parity": parity,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "parity": parity, "exchange": exchange,
+            "layout": {"n_side_relabelled_by_popularity": relabelled, "gathers_served_from_shared_memory_prefix": hot_fraction},
             "solve": {"lanczos_steps": res.diagnostics.lanczos_steps, "n_opb": int(n_opb), "n_opb_run": int(res.profile["n_opb"]),
                       "n_spmv_run": int(res.profile["n_spmv"]),
                       "ritz_values_stabilized": res.diagnostics.ritz_values_stabilized, "d": res.d,

@@ -190,6 +190,12 @@ SVDLAS2_API int svdlas2_operator_time_opb(svdlas2_operator *op, int reps, int fl
  * and collective staging), exactly like a `&mut` borrow in the reference's language. */
 SVDLAS2_API int svdlas2_operator_set(svdlas2_operator *op, const char *knob, int64_t value);
 
+/* read-only facts about a resident operator (reporting): "relabelled" (1 when the N side was re-numbered by popularity at
+ * upload), "ring" (1 when the sharded exchange runs as the peer-memory kernel, 0 = ncclAllReduce / single GPU),
+ * "ring_calls", "ring_two_shot_calls", "ring_bytes_per_call" (bytes this rank moves over NVLink per exchange),
+ * "hot_fraction" (share of B's gathers served from the shared-memory prefix).  Unknown keys return an error. */
+SVDLAS2_API int svdlas2_operator_info(const svdlas2_operator *op, const char *key, double *value);
+
 /* ---- multi-GPU, one process per GPU (rows of the oriented operator B sharded by nnz) -- */
 
 #define SVDLAS2_COMM_ID_BYTES 128

@@ -6,7 +6,6 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import svdlibrs_b200 as las2
 from svdlibrs_b200 import synthetic
 
 ap = argparse.ArgumentParser()
@@ -18,9 +17,14 @@ ap.add_argument("--flush", type=int, default=0)
 ap.add_argument("--hot", type=int, default=-1)
 ap.add_argument("--shard", type=int, default=1, help="profile the first of this many row shards (multi-GPU shard shape)")
 a = ap.parse_args()
-A, dims = synthetic.make(a.workload, scale=a.scale)
+try:
+    cores = len(os.sched_getaffinity(0))
+except Exception:
+    cores = os.cpu_count() or 1
+A, dims = synthetic.make(a.workload, scale=a.scale, workers=min(32, cores))  # forked generator workers: before CUDA starts
 if a.shard > 1:
     A = A[: A.shape[0] // a.shard].tocsr()
+import svdlibrs_b200 as las2
 with las2.Operator(A) as op:
     op.set("spmv_variant", a.variant)
     op.set("spmv_hot", a.hot)

@@ -14,14 +14,9 @@ ap.add_argument("--solves", type=int, default=2); ap.add_argument("--dims", type
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-import torch
-torch.cuda.set_device(local)
 import svdlibrs_b200 as las2
 from svdlibrs_b200 import sharding, synthetic
 dist = None
-if world > 1:
-    import torch.distributed as dist
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 cfg = synthetic.CONFIGS[a.workload]
 assert cfg["kind"] == "powerlaw" and cfg["fmt"] == "csr" and cfg["ncols"] < 1.2 * cfg["nrows"], "row-sharded generator: tall power-law CSR configs"
@@ -33,9 +28,18 @@ offs = np.concatenate([[0], np.cumsum(lens)])
 bounds = sharding.partition_rows_by_nnz(offs, world)
 lo, hi = int(bounds[rank]), int(bounds[rank + 1])
 t0 = time.time()
-Bl = synthetic.powerlaw_csr(nrows, ncols, nnz_req, 12345, rows=(lo, hi))
+try:
+    cores = len(os.sched_getaffinity(0))
+except Exception:
+    cores = os.cpu_count() or 1
+Bl = synthetic.powerlaw_csr(nrows, ncols, nnz_req, 12345, rows=(lo, hi), workers=max(1, min(16, cores // world)))
 gen_s = time.time() - t0
 nnz_local = int(Bl.nnz)
+import torch  # CUDA starts only now: the generator forked its workers above
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 if world > 1:
     t = torch.tensor([nnz_local], device="cuda", dtype=torch.int64); dist.all_reduce(t); nnz_global = int(t.item())
     comm = las2.Communicator(rank, world, sharding.broadcast_comm_id(dist, rank), device=local)
@@ -69,7 +73,8 @@ with las2.ShardedOperator(Bl, nrows, lo, nnz_global, comm, False, device=local) 
                sigma0=float(last.s[0]) if last.d else None, sigma_last=float(last.s[-1]) if last.d else None, ortho_defect8=ortho,
                ms_per_opb=round(vmax(tm["ms_per_opb"]), 4), ms_spmv_b=round(tm["ms_spmv_b"], 4), ms_spmv_bt=round(tm["ms_spmv_bt"], 4),
                opb_bytes_local=tm["bytes_opb"], purge_fired=int(last.profile["n_purge_fired"]), purge_vectors=int(last.profile["n_purge_vectors"]),
-               local_rows=[lo, hi], local_nnz=nnz_local)
+               local_rows=[lo, hi], local_nnz=nnz_local, ring=bool(op.info("ring")) if world > 1 else None,
+               ring_env=os.environ.get("SVDLAS2_RING", ""))
     if rank == 0:
         print("SCALE " + json.dumps(rec), flush=True)
         if a.out:

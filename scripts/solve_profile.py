@@ -7,7 +7,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2"); ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--reps", type=int, default=3); ap.add_argument("--dims", type=int, default=0)
 a = ap.parse_args()
-A, dims = synthetic.make(a.workload, scale=a.scale)
+try:
+    cores = len(os.sched_getaffinity(0))
+except Exception:
+    cores = os.cpu_count() or 1
+A, dims = synthetic.make(a.workload, scale=a.scale, workers=min(32, cores))
 dims = a.dims or dims
 with las2.Operator(A) as op:
     for i in range(a.reps):

@@ -253,6 +253,14 @@ class Operator:
         if rc != 0:
             _raise(rc)
 
+    def info(self, key: str) -> float:
+        """Read-only facts about the resident operator (svdlas2_operator_info): "relabelled", "ring", "ring_calls", ..."""
+        v = C.c_double()
+        rc = _lib.lib().svdlas2_operator_info(self._h, key.encode(), C.byref(v))
+        if rc != 0:
+            _raise(rc)
+        return v.value
+
     def solve(self, dimensions=0, iterations=0, end_interval=(-1.0e-30, 1.0e-30), kappa=1.0e-6,
               random_seed=0) -> SvdRec:
         endi = (C.c_double * 2)(float(end_interval[0]), float(end_interval[1]))

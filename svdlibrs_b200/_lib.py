@@ -52,6 +52,7 @@ SYMBOLS = [
     "svdlas2_trim_caches",
     "svdlas2_operator_create", "svdlas2_operator_destroy", "svdlas2_operator_solve", "svdlas2_operator_opa",
     "svdlas2_operator_opb", "svdlas2_operator_shape", "svdlas2_operator_time_opb", "svdlas2_operator_set",
+    "svdlas2_operator_info",
     "svdlas2_comm_unique_id", "svdlas2_comm_create", "svdlas2_comm_destroy", "svdlas2_operator_create_shard",
 ]
 
@@ -110,6 +111,8 @@ def lib():
     L.svdlas2_operator_time_opb.restype = C.c_int
     L.svdlas2_operator_set.argtypes = [OP, C.c_char_p, C.c_int64]
     L.svdlas2_operator_set.restype = C.c_int
+    L.svdlas2_operator_info.argtypes = [OP, C.c_char_p, C.POINTER(C.c_double)]
+    L.svdlas2_operator_info.restype = C.c_int
     L.svdlas2_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.svdlas2_comm_unique_id.restype = C.c_int
     L.svdlas2_comm_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_void_p)]

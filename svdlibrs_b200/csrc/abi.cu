@@ -469,6 +469,26 @@ int svdlas2_test_ring_emulation(int G, uint64_t n, const double *ys, const doubl
     });
 }
 
+int svdlas2_operator_info(const svdlas2_operator *op_, const char *key, double *value) {
+    const Operator *op = reinterpret_cast<const Operator *>(op_);
+    if (!op || !key || !value) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
+    const PeerRing *R = op->ring.get();
+    const u64 ld = (op->N + 31) / 32 * 32;
+    if (!std::strcmp(key, "relabelled")) { *value = op->relabel.active ? 1.0 : 0.0; return SVDLAS2_OK; }
+    if (!std::strcmp(key, "ring")) { *value = R ? 1.0 : 0.0; return SVDLAS2_OK; }
+    if (!std::strcmp(key, "ring_calls")) { *value = R ? (double)R->calls : 0.0; return SVDLAS2_OK; }
+    if (!std::strcmp(key, "ring_two_shot_calls")) { *value = R ? (double)R->two_shot_calls : 0.0; return SVDLAS2_OK; }
+    if (!std::strcmp(key, "ring_bytes_per_call")) {
+        // one-shot: reads G-1 whole partial vectors; two-shot: reads G-1 slices of N/G and pushes its slice to G-1 peers
+        double b = 0.0;
+        if (R) b = (ld * 8 > R->two_shot_min_bytes) ? 2.0 * (R->G - 1) * (double)ld * 8.0 / R->G : (double)(R->G - 1) * (double)ld * 8.0;
+        *value = b;
+        return SVDLAS2_OK;
+    }
+    if (!std::strcmp(key, "hot_fraction")) { *value = op->B.hot_fraction; return SVDLAS2_OK; }
+    return fail(SVDLAS2_ERR_INVALID_ARGUMENT, std::string("unknown key ") + key);
+}
+
 int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value) {
     Operator *op = reinterpret_cast<Operator *>(op_);
     if (!op || !knob) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");

@@ -22,6 +22,12 @@ def n_gpus():
         return 0
 
 
+def ranks_per_test():
+    """ranks per test: min(GPUs, 4) unless SVDLAS2_TEST_WORLD says otherwise (the 8-GPU log of profiles/)"""
+    w = int(os.environ.get("SVDLAS2_TEST_WORLD", "0"))
+    return min(n_gpus(), w if w > 1 else 4)
+
+
 def free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -45,7 +51,7 @@ def test_sharded_solve_matches_single_gpu_and_oracle(workload, scale, dims, shar
         monkeypatch.setenv("SVDLAS2_SHARD_PURGE_MB", shard_purge_mb)
         monkeypatch.setenv("SVDLAS2_SHARD_RITZ_GFLOP", "0")  # and the Ritz contraction as well
         monkeypatch.setenv("SVDLAS2_TRACE", "1")
-    world = min(n_gpus(), 4)
+    world = ranks_per_test()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py"),
            "--workload", workload, "--scale", str(scale), "--dims", str(dims), "--oracle", "1"]
@@ -72,7 +78,7 @@ def test_seed_zero_is_shared_by_all_ranks():
     build different start vectors and the replicated state diverges (silently wrong sums, mismatched collectives)."""
     if n_gpus() < 2:
         pytest.skip("needs at least 2 GPUs")
-    world = min(n_gpus(), 4)
+    world = ranks_per_test()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py"),
            "--workload", "cfg2", "--scale", "0.03", "--dims", "20", "--oracle", "1", "--seed", "0"]
