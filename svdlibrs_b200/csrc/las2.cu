@@ -62,6 +62,12 @@ struct Solver {
     PartialSlot slot[8];
     PinnedBuf<double> hs;
     PanelWork pw;
+    // the step chain (vecops.cuh): partial scratch, call counter, and the panel column the chain has already filled with
+    // the next Lanczos vector (none: ~0)
+    DevBuf<double> chain_work;
+    unsigned long long chain_seq = 0;
+    u64 spec_col = ~(u64)0;
+    bool use_chain = false;
     // host (WorkSpace arrays, src/lib.rs:770-775)
     std::vector<double> alf, bet, eta, oldeta, ritz, bnd, w5;
     svdlas2_profile prof;
@@ -83,6 +89,12 @@ struct Solver {
         parts.alloc(8 * (size_t)kMaxParts);
         for (int i = 0; i < 8; i++) slot[i] = PartialSlot{parts.get() + (size_t)i * kMaxParts, 0};
         hs.alloc(16);
+        for (int i = 0; i < 16; i++) hs[i] = 0.0;
+        {
+            const char *e = std::getenv("SVDLAS2_STEP_CHAIN");
+            use_chain = (e && e[0] == '1') && step_chain_max_grid() > 0; // opt-in until validated on the GPU
+            if (use_chain) chain_work.alloc(5 * (size_t)kMaxParts);
+        }
         alf.assign(iters, 0.0); eta.assign(iters, 0.0); oldeta.assign(iters, 0.0);
         bet.assign(iters + 1, 0.0); ritz.assign(iters + 1, 0.0);
         bnd.assign(iters + 1, 1.7976931348623157e308); // f64::MAX, :775
@@ -167,6 +179,26 @@ struct Solver {
     }
 
     Coef sum_of(int w) const { return Coef::partials(slot[w].parts, slot[w].nparts); }
+
+    // wait for the step chain's scalars: the kernel's last act is a sequence number in pinned memory (no stream sync)
+    void wait_chain(double *out) {
+        volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(hs.get() + 4);
+        const double tw0 = wall();
+        u64 spins = 0;
+        while (*flag != chain_seq) {
+            if ((++spins & 0xfff) == 0) {
+                const cudaError_t e = cudaStreamQuery(s);
+                if (e != cudaSuccess && e != cudaErrorNotReady) LAS2_CUDA(e);
+                if (e == cudaSuccess && *flag != chain_seq) { // finished without delivering: a launch failure
+                    LAS2_CUDA(cudaGetLastError());
+                    if (*flag != chain_seq) throw Error(SVDLAS2_ERR_CUDA, "step chain finished without its scalars");
+                }
+            }
+        }
+        prof.t_sync_wait += wall() - tw0;
+        prof.n_host_syncs += 1;
+        for (int i = 0; i < 4; i++) out[i] = hs[i];
+    }
 
     // ---- startv (src/lib.rs:1098-1147): r <- B'B(random); on a restart also swept against q_0..q_{step-1} ----
     double startv(u64 step, uint32_t seed) {
@@ -290,7 +322,8 @@ struct Solver {
             // take a lanczos step
             ensure_cols(j + 1);
             const double rn = *rnm;
-            vec_scale(q(j), r.get(), 1.0 / rn, ld, s);
+            if (spec_col != j) vec_scale(q(j), r.get(), 1.0 / rn, ld, s); // (else: the previous step's chain already wrote it)
+            spec_col = ~(u64)0;
             qused = j + 1;
             int ns = 0; // slots in use for this step
             // r = B'B q_j - rnm q_{j-1} ; alf = r . q_j  (sharded: the all-reduce, the update and the dot are ONE kernel)
@@ -303,6 +336,34 @@ struct Solver {
                 gather({s_alf}, &a);
                 if (std::fabs(alf[j - 1]) > 4.0 * std::fabs(a)) *ll = j;
             }
+            double v[4];
+            const u64 purges_before = prof.n_purge_fired;
+            if (use_chain && j > kMaxLL) {
+                // ---- :1279-1304 as ONE cooperative launch (vec_step_chain), scalars through pinned memory ----
+                const u64 lim = std::min<u64>(j - 1, *ll);
+                const bool speculate = j + 1 < last;
+                if (speculate) ensure_cols(j + 2);
+                StepChain c;
+                c.nphases = (int)lim + 3;
+                c.x[0] = q(j);
+                c.y[0] = lim > 0 ? q(0) : q(j - 1);
+                for (u64 i = 1; i <= lim; i++) {
+                    c.x[i] = q(i - 1);
+                    c.y[i] = i < lim ? q(i) : q(j - 1);
+                    eta[i - 1] = eps1;
+                    oldeta[i - 1] = eps1;
+                }
+                c.x[lim + 1] = q(j - 1); c.y[lim + 1] = q(j);
+                c.x[lim + 2] = q(j);     c.y[lim + 2] = nullptr;
+                c.pick[0] = 0; c.pick[1] = (int)lim + 1; c.pick[2] = (int)lim + 2; c.pick[3] = 0;
+                c.alf_parts = slot[s_alf].parts; c.alf_nparts = slot[s_alf].nparts;
+                c.q_next = speculate ? q(j + 1) : nullptr;
+                chain_seq += 1;
+                vec_step_chain(r.get(), ld, c, chain_work.get(), hs.get(), chain_seq, s);
+                prof.n_kernel_launches += 1;
+                wait_chain(v);
+                if (speculate) spec_col = j + 1;
+            } else {
             // r -= alf q_j, then orthogonalize against the first ll Lanczos vectors (:1285-1292) ...
             const double *ax = q(j);
             int prev = s_alf;
@@ -326,8 +387,8 @@ struct Solver {
             const int s_nrm = ns++;
             prof.n_kernel_launches += 3;
             (void)s_ll;
-            double v[4];
             gather({s_alf, s_t1, s_t2, s_nrm}, v); // the one read-back of this step
+            }
             const double nrm2 = v[3];
             alf[j] = v[0];
             if (bet[j] > 0.0) bet[j] += v[1];
@@ -338,7 +399,8 @@ struct Solver {
 
             ortbnd(j, *rnm);                 // update the orthogonality bounds
             purge(*ll, j, rnm, *tol);        // restore the orthogonality state when needed
-            if (*rnm <= *tol) *rnm = 0.0;
+            if (prof.n_purge_fired != purges_before) spec_col = ~(u64)0; // r changed: the speculative q_{j+1} is stale
+            if (*rnm <= *tol) { *rnm = 0.0; spec_col = ~(u64)0; }
             j += 1;
         }
         return j;

@@ -2,6 +2,10 @@
 // All kernels are HBM/L2-bound streams over N-vectors: 128-bit loads, grid capped at 4 CTAs per SM.
 #include "vecops.cuh"
 
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 namespace las2 {
 
 namespace {
@@ -131,6 +135,63 @@ __global__ void k_gather_scalars(GatherList g, double *__restrict__ out) {
     }
 }
 
+__global__ void __launch_bounds__(kVecThreads)
+k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, double *__restrict__ work, double *__restrict__ host_out,
+             unsigned long long seq) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[kVecThreads / 32];
+    __shared__ double cs;
+    double coef_seen[5];
+    const double *parts = c.alf_parts;
+    int nparts = c.alf_nparts;
+    for (int k = 0; k < c.nphases; k++) {
+        const double coef = cta_sum_partials(parts, nparts, &cs);
+        coef_seen[k] = coef;
+        const double nc = -coef;
+        const double2 *__restrict__ x = reinterpret_cast<const double2 *>(c.x[k]);
+        const double2 *__restrict__ y = reinterpret_cast<const double2 *>(c.y[k]);
+        double acc = 0.0;
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (u64)gridDim.x * blockDim.x) {
+            double2 rv = r[i];
+            const double2 xv = x[i];
+            rv.x = __dadd_rn(rv.x, __dmul_rn(nc, xv.x)); // svd_daxpy(-c, x, r)
+            rv.y = __dadd_rn(rv.y, __dmul_rn(nc, xv.y));
+            r[i] = rv;
+            const double2 yv = y ? (c.y[k] == c.x[k] ? xv : y[i]) : rv;
+            acc = fma(rv.x, yv.x, acc);
+            acc = fma(rv.y, yv.y, acc);
+        }
+        __syncthreads(); // sm / cs are reused by the next phase
+        const double t = cta_reduce(acc, sm);
+        double *out = work + (size_t)k * kMaxParts;
+        if (threadIdx.x == 0) out[blockIdx.x] = t;
+        parts = out;
+        nparts = (int)gridDim.x;
+        grid.sync();
+    }
+    const double nrm2 = cta_sum_partials(parts, nparts, &cs);
+    if (c.q_next) {
+        // q_{j+1} = r / rnm exactly as the host-launched k_scale would form it (rnm = sqrt(|r|^2), alpha = 1 / rnm)
+        const double alpha = 1.0 / sqrt(nrm2);
+        double2 *__restrict__ qn = reinterpret_cast<double2 *>(c.q_next);
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (u64)gridDim.x * blockDim.x) {
+            double2 v = r[i];
+            v.x = __dmul_rn(alpha, v.x);
+            v.y = __dmul_rn(alpha, v.y);
+            qn[i] = v;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        host_out[0] = coef_seen[c.pick[0]];
+        host_out[1] = coef_seen[c.pick[1]];
+        host_out[2] = coef_seen[c.pick[2]];
+        host_out[3] = nrm2;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(host_out + 4) = seq;
+    }
+}
+
 // out[i * n + c] = V[i * ld + old2new[c]]: the N-side singular vectors back in the caller's numbering (coalesced writes)
 __global__ void __launch_bounds__(kVecThreads)
 k_unpermute_rows(const double *__restrict__ V, u64 ld, u64 n, const u32 *__restrict__ old2new, double *__restrict__ out) {
@@ -151,6 +212,35 @@ void unpermute_rows(const double *V, u64 ld, u64 n, u32 d, const u32 *old2new, d
         k_unpermute_rows<<<dim3(gx, nd), kVecThreads, 0, s>>>(V + (u64)d0 * ld, ld, n, old2new, out + (u64)d0 * n);
     }
     LAS2_LAUNCH_CHECK();
+}
+
+unsigned step_chain_max_grid() {
+    static unsigned cached[kMaxDevicesTracked];
+    static bool known[kMaxDevicesTracked];
+    const int slot = current_device_slot();
+    if (!known[slot]) {
+        int dev = 0, coop = 0, per_sm = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_chain, kVecThreads, 0) == cudaSuccess)
+            cached[slot] = (unsigned)std::min(kMaxParts, per_sm * sms);
+        else
+            cached[slot] = 0;
+        cudaGetLastError();
+        known[slot] = true;
+    }
+    return cached[slot];
+}
+
+void vec_step_chain(double *r, u64 ld, const StepChain &c, double *work, double *host_out, unsigned long long seq, cudaStream_t s) {
+    u64 n2 = ld / 2;
+    unsigned grid = std::min<unsigned>(step_chain_max_grid(), vec_grid(ld));
+    if (grid == 0) throw Error(SVDLAS2_ERR_CUDA, "cooperative launch unavailable");
+    StepChain cc = c;
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    void *args[] = {&r2, &n2, &cc, &work, &host_out, &seq};
+    LAS2_CUDA(cudaLaunchCooperativeKernel((const void *)k_step_chain, dim3(grid), dim3(kVecThreads), args, 0, s));
 }
 
 unsigned vec_grid(u64 ld) {

@@ -46,6 +46,26 @@ void vec_axpy_dot(double *r, const double *x, Coef coef, const double *y, u64 ld
 // r -= coef * x                                       (svd_daxpy, :840-844)
 void vec_axpy(double *r, const double *x, Coef coef, u64 ld, cudaStream_t s);
 
+// The local re-orthogonalisation chain of one Lanczos step (reference src/lib.rs:1279-1304) as ONE cooperative launch:
+//   phase k:  c_k = canonical sum of the previous phase's partials (phase 0: the alf partials of the opb epilogue) ;
+//             r -= c_k * x_k ;  partials of  r . y_k   (y_k == nullptr: r . r)
+// with a grid-wide barrier between the phases, instead of 3-5 dependent launches of k_axpy_dot plus k_gather_scalars.  The
+// last CTA out writes the scalars the host needs (alf, t1, t2, |r|^2 -- out[0..4) in that order, see `pick`) to pinned host
+// memory, followed by a sequence number the host polls: no cudaStreamSynchronize per step.  Optionally also writes the next
+// Lanczos vector q_next = r / sqrt(|r|^2) (the host discards it when purge / a restart changes r).
+struct StepChain {
+    int nphases;              // 3 .. 5
+    const double *x[5];       // axpy vectors
+    const double *y[5];       // dot vectors (nullptr: the norm)
+    int pick[4];              // which phase's coefficient goes to out[0], out[1], out[2]; out[3] is always the final norm^2
+    const double *alf_parts;  // partials of the coefficient of phase 0
+    int alf_nparts;
+    double *q_next;           // may be nullptr
+};
+// work: 5 * kMaxParts doubles of partial scratch + 2 unsigned ints; host_out: 4 doubles + 1 sequence word (pinned).
+void vec_step_chain(double *r, u64 ld, const StepChain &c, double *work, double *host_out, unsigned long long seq, cudaStream_t s);
+unsigned step_chain_max_grid(); // co-resident CTAs of the chain kernel on the current device (0: cooperative launch unavailable)
+
 // Sum up to 8 partial slots with the canonical reduction and write the scalars to `out` (pinned host memory
 // or device memory).
 struct GatherList {

@@ -576,3 +576,25 @@ def test_ritz_contraction_variants_agree(las2, n, js, d):
     rc = L.svdlas2_test_time_ritz(n, js, d, 1, -1, ms, C.byref(diff), C.byref(err))
     assert rc == 0, L.svdlas2_last_error()
     assert diff.value <= 1e-13 * js ** 0.5 and err.value <= 1e-13 * js ** 0.5, (diff.value, err.value)
+
+
+def test_step_chain_matches_oracle_and_the_kernel_chain(las2, oracle, monkeypatch):
+    """The local re-orthogonalisation of a Lanczos step (reference src/lib.rs:1279-1304) as ONE cooperative launch with the
+    scalars polled from pinned memory and the next Lanczos vector written speculatively (vec_step_chain), against the oracle
+    and against the chain of separate kernels: identical counts, sigma to 1e-10, vectors to 1 - 1e-8; covers ll = 0 and
+    ll > 0 (extra phases), purge steps (speculation discarded) and the restart path."""
+    from svdlibrs_b200 import synthetic
+    cases = [(synthetic.make("cfg1")[0], 20), (synthetic.make("cfg2", scale=0.02)[0], 30), (synthetic.make("cfg3", scale=0.01)[0], 15),
+             (sp.random(400, 300, density=0.05, format="csr", random_state=3), 10),
+             (sp.coo_matrix(([3.0, 4.0], ([1, 2], [0, 1])), shape=(4, 4)).tocsr(), 3), (sp.identity(3, format="csc"), 0)]
+    for A, dims in cases:
+        monkeypatch.setenv("SVDLAS2_STEP_CHAIN", "0")
+        plain = las2.svd_dim_seed(A, dims, 12345)
+        monkeypatch.setenv("SVDLAS2_STEP_CHAIN", "1")
+        got = las2.svd_dim_seed(A, dims, 12345)
+        ref = oracle.svd_dim_seed(A, dims, 12345)
+        assert_svd_parity(got, ref)
+        assert got.diagnostics == plain.diagnostics
+        assert np.allclose(got.s, plain.s, rtol=1e-12, atol=0)
+        if min(A.shape) > 100:
+            assert got.profile["n_kernel_launches"] < plain.profile["n_kernel_launches"]
