@@ -439,7 +439,7 @@ def run_ours(args):
 
         def make_resident():
             op_ = las2.ShardedOperator(B_host, W.m_global, W.row_begin, W.nnz, comm, W.transposed, device=local)
-            op_.set("nside_on_rank0_only", 1)  # V is replicated: only rank 0 brings it to the host (U comes out row-sliced per rank)
+            op_.set("nside_mode", 2)  # V is replicated: every rank brings 1/G of its rows to the host (U comes out row-sliced per rank)
             return op_
 
         def e2e_call():

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SVDLAS2_ABI_VERSION 1
+#define SVDLAS2_ABI_VERSION 2
 
 #if defined(__GNUC__) || defined(__clang__)
 #define SVDLAS2_API __attribute__((visibility("default")))
@@ -112,6 +112,12 @@ typedef struct svdlas2_result {
     double *bet;        /* trace_len + 1 */
     double *ritz;       /* trace_len */
     double *bnd;        /* trace_len */
+    /* Sharded operators only: which of the d N-side vectors (rows of vt, or of ut on the transposed path) this rank's result
+     * holds: rows [nside_row_begin, nside_row_begin + nside_row_count), stored from the array's first row on.  Everywhere
+     * else: 0 and d.  (Knob "nside_mode": 0 = every rank downloads all of them, 1 = rank 0 only, 2 = the rows are dealt
+     * out in contiguous blocks over the ranks, so that no rank moves more than 1/G of the replicated vectors over PCIe.) */
+    uint64_t nside_row_begin;
+    uint64_t nside_row_count;
 } svdlas2_result;
 
 /* ---- one-shot entry points (what a Rust shim's svdLAS2 binds) --------------- */
@@ -179,9 +185,10 @@ SVDLAS2_API int svdlas2_operator_shape(const svdlas2_operator *op, uint64_t *m, 
 SVDLAS2_API int svdlas2_operator_time_opb(svdlas2_operator *op, int reps, int flush_l2, double *ms_per_opb,
                               double *ms_spmv_b, double *ms_spmv_bt);
 
-/* knobs: "profile" (0/1: per-opb CUDA events); "nside_on_rank0_only" (0/1, sharded operators: the N-side singular
- * vectors are replicated over the ranks, so on request only rank 0 downloads them and the other ranks return an
- * N-side array of zero columns; the M-side vectors always come out row-sliced per rank); tuning / test overrides
+/* knobs: "profile" (0/1: per-opb CUDA events); "nside_mode" (sharded operators: the N-side singular vectors are replicated
+ * over the ranks; 0 = every rank downloads all of them, 1 = only rank 0 does and the other ranks return an N-side array of
+ * zero columns, 2 = every rank downloads its contiguous block of them, see svdlas2_result.nside_row_begin; the M-side
+ * vectors always come out row-sliced per rank); "nside_on_rank0_only" (0/1) = nside_mode 0 / 1; tuning / test overrides
  * of the SpMV: "spmv_variant" (-1 auto, 5 = warp-chunk stream, 0..3 = the tile kernels on the natural CSR arrays),
  * "spmv_hot", "spmv_shape", "spmv_pdl", "spmv_carveout", "spmv_smem_pad_kb".  Every knob is stored in the operator it
  * is set on; nothing is process-wide.

@@ -39,6 +39,8 @@ pub struct svdlas2_result {
     pub bet: *mut f64,
     pub ritz: *mut f64,
     pub bnd: *mut f64,
+    pub nside_row_begin: u64,
+    pub nside_row_count: u64,
 }
 
 pub const OK: c_int = 0;

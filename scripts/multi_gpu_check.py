@@ -15,6 +15,7 @@ ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--scale", type=float, default=0.05)
 ap.add_argument("--dims", type=int, default=30)
 ap.add_argument("--oracle", type=int, default=0)
+ap.add_argument("--nside-mode", type=int, default=0, help="2: the replicated N-side vectors are dealt out by rows over the ranks")
 ap.add_argument("--seed", type=int, default=12345, help="0: the library draws the seed (rank 0's draw must reach every rank)")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -27,6 +28,7 @@ Bl, lo, hi = sharding.local_shard(B, bounds, rank)
 comm = las2.Communicator(rank, world, sharding.broadcast_comm_id(dist, rank), device=local)
 t0 = time.time()
 with las2.ShardedOperator(Bl, B.shape[0], lo, int(B.nnz), comm, transposed, device=local) as op:
+    op.set("nside_mode", a.nside_mode)
     r = op.solve(a.dims, random_seed=a.seed)
     t_sharded = time.time() - t0
     seed_used = r.diagnostics.random_seed
@@ -41,8 +43,17 @@ sig = torch.tensor(r.s, device="cuda")
 ref = sig.clone(); dist.broadcast(ref, 0)
 same_s = bool(torch.equal(sig, ref))
 nside = r.ut if transposed else r.vt
-v0 = torch.tensor(nside, device="cuda"); vr = v0.clone(); dist.broadcast(vr, 0)
-same_v = bool(torch.equal(v0, vr))
+if a.nside_mode == 2:
+    # every rank holds a contiguous block of the rows: re-assemble them (in rank order) on every rank
+    blocks = [None] * world
+    dist.all_gather_object(blocks, (r.nside_rows[0], np.array(nside)))
+    blocks.sort(key=lambda b: b[0])
+    assert [b[0] for b in blocks] == [r.d * g // world for g in range(world)] and sum(b[1].shape[0] for b in blocks) == r.d
+    nside = np.concatenate([b[1] for b in blocks], axis=0)
+    same_v = True
+else:
+    v0 = torch.tensor(nside, device="cuda"); vr = v0.clone(); dist.broadcast(vr, 0)
+    same_v = bool(torch.equal(v0, vr))
 # gather the M-side slices on rank 0
 mside = r.vt if transposed else r.ut
 parts = [None] * world

@@ -53,7 +53,7 @@ def vmax(x):
 t0 = time.time()
 with las2.ShardedOperator(Bl, nrows, lo, nnz_global, comm, False, device=local) as op:
     upload_s = vmax(time.time() - t0)
-    op.set("nside_on_rank0_only", 1)  # V is replicated: only rank 0 brings it to the host (U comes out row-sliced per rank)
+    op.set("nside_mode", int(os.environ.get("NSIDE_MODE", "2")))  # V is replicated: every rank downloads 1/G of its rows
     del Bl
     recs = []
     for i in range(a.solves):

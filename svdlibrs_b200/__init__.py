@@ -78,6 +78,7 @@ class SvdRec:
     vt: np.ndarray
     diagnostics: Diagnostics
     profile: dict = field(default_factory=dict, compare=False)
+    nside_rows: tuple = field(default=(0, 0), compare=False)  # sharded operators: (first, count) of the N-side rows held here
     trace: dict = field(default_factory=dict, compare=False)
 
     def recompose(self) -> np.ndarray:
@@ -169,8 +170,11 @@ def _take_result(ptr) -> SvdRec:
     owner = _ResultOwner(ptr)
     r = ptr.contents
     d = int(r.d)
-    ut = _view(owner, r.ut, (d, int(r.ut_cols)))
-    vt = _view(owner, r.vt, (d, int(r.vt_cols)))
+    # a sharded operator may hand out only a block of the (replicated) N-side vectors per rank: svdlas2_result.nside_row_*
+    nb, nc = int(r.nside_row_begin), int(r.nside_row_count)
+    n_is_ut = bool(r.diagnostics.transposed)
+    ut = _view(owner, r.ut, (nc if n_is_ut else d, int(r.ut_cols)))
+    vt = _view(owner, r.vt, (d if n_is_ut else nc, int(r.vt_cols)))
     s = _view(owner, r.s, (d,)).copy()
     g = r.diagnostics
     diag = Diagnostics(int(g.non_zero), int(g.dimensions), int(g.iterations), bool(g.transposed),
@@ -183,7 +187,9 @@ def _take_result(ptr) -> SvdRec:
     if n and r.alf:
         trace = dict(alf=_view(owner, r.alf, (n,)).copy(), bet=_view(owner, r.bet, (n + 1,)).copy(),
                      ritz=_view(owner, r.ritz, (n,)).copy(), bnd=_view(owner, r.bnd, (n,)).copy())
-    return SvdRec(d, ut, s, vt, diag, prof, trace)
+    rec = SvdRec(d, ut, s, vt, diag, prof, trace)
+    rec.nside_rows = (nb, nc)
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------ public API

@@ -43,6 +43,7 @@ class Result(C.Structure):
         ("ut", f64p), ("s", f64p), ("vt", f64p),
         ("diagnostics", Diagnostics), ("profile", Profile),
         ("trace_len", C.c_uint64), ("alf", f64p), ("bet", f64p), ("ritz", f64p), ("bnd", f64p),
+        ("nside_row_begin", C.c_uint64), ("nside_row_count", C.c_uint64),
     ]
 
 

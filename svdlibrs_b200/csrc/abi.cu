@@ -493,7 +493,12 @@ int svdlas2_operator_set(svdlas2_operator *op_, const char *knob, int64_t value)
     Operator *op = reinterpret_cast<Operator *>(op_);
     if (!op || !knob) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
     if (!std::strcmp(knob, "profile")) { op->profile = value != 0; return SVDLAS2_OK; }
-    if (!std::strcmp(knob, "nside_on_rank0_only")) { op->nside_on_rank0_only = value != 0; return SVDLAS2_OK; }
+    if (!std::strcmp(knob, "nside_on_rank0_only")) { op->nside_mode = value != 0 ? 1 : 0; return SVDLAS2_OK; }
+    if (!std::strcmp(knob, "nside_mode")) {
+        if (value < 0 || value > 2) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "nside_mode must be 0, 1 or 2");
+        op->nside_mode = (int)value;
+        return SVDLAS2_OK;
+    }
     // SpMV tuning: stored in THIS operator's two matrices (no process-wide state)
     auto both = [&](int SpmvTuning::*field) { op->B.tune.*field = (int)value; op->BT.tune.*field = (int)value; return SVDLAS2_OK; };
     if (!std::strcmp(knob, "spmv_variant")) return both(&SpmvTuning::variant);

@@ -72,6 +72,7 @@ struct Solver {
     std::vector<double> alf, bet, eta, oldeta, ritz, bnd, w5;
     svdlas2_profile prof;
     u64 n_sharded_sweeps = 0; // purge / restart sweeps whose rows were split over the ranks
+    double t_purge_host = 0.0, t_analysis_host = 0.0; // SVDLAS2_TRACE: host time inside purge (incl. its syncs) / the analyses of T
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> opb_events;
     // result buffers (pinned, from the host pool) are acquired on a helper thread while the GPU runs lanso
     cudaStream_t copy_stream = nullptr;
@@ -103,8 +104,10 @@ struct Solver {
         const u64 want = dims * (M + N) * sizeof(double);
         if (want <= host_prefetch_limit() && !std::getenv("SVDLAS2_NO_PREFETCH")) { // only when the upper bound d <= dims is affordable
             const int dev = op.device;
-            const bool skip_n = op.comm && op.nside_on_rank0_only && op.comm->rank() != 0;
-            const size_t bm = std::max<u64>(1, dims * M) * sizeof(double), bn = std::max<u64>(1, skip_n ? 0 : dims * N) * sizeof(double);
+            u64 vb0 = 0, ve0 = 0;
+            op.nside_rows(dims, &vb0, &ve0); // upper bound: d <= dims (a block of the dealt-out rows never exceeds this)
+            const u64 vrows = op.nside_mode == 2 && op.comm ? (dims + op.comm->world() - 1) / op.comm->world() + 1 : ve0 - vb0;
+            const size_t bm = std::max<u64>(1, dims * M) * sizeof(double), bn = std::max<u64>(1, vrows * N) * sizeof(double);
             fut_m = std::async(std::launch::async, [dev, bm] { cudaSetDevice(dev); return host_acquire(bm); });
             fut_n = std::async(std::launch::async, [dev, bn] { cudaSetDevice(dev); return host_acquire(bn); });
             prefetched = true;
@@ -398,7 +401,9 @@ struct Solver {
             *tol = std::sqrt(kEps) * anorm;
 
             ortbnd(j, *rnm);                 // update the orthogonality bounds
+            const double tp0 = wall();
             purge(*ll, j, rnm, *tol);        // restore the orthogonality state when needed
+            t_purge_host += wall() - tp0;
             if (prof.n_purge_fired != purges_before) spec_col = ~(u64)0; // r changed: the speculative q_{j+1} is stale
             if (*rnm <= *tol) { *rnm = 0.0; spec_col = ~(u64)0; }
             j += 1;
@@ -426,6 +431,8 @@ struct Solver {
             bet[first] = rnm;
 
             // analyze T: eigenvalues + last-row eigenvector components of every unreduced block
+            const double ta0 = wall();
+            struct TAcc { double &acc; double t0; ~TAcc() { acc += wall() - t0; } } tacc{t_analysis_host, ta0};
             u64 l = 0;
             for (u64 id2 = 0; id2 < j; id2++) {
                 if (l > j) break;
@@ -503,14 +510,18 @@ struct Solver {
         const u64 mcols = M;
         // the N-side vectors are replicated over the ranks of a sharded run: on request only rank 0 downloads them
         // (the other ranks return an N-side array of zero columns)
-        const bool skip_n = op.comm && op.nside_on_rank0_only && op.comm->rank() != 0;
-        const u64 ncols = skip_n ? 0 : N;
+        u64 vb = 0, ve = 0;
+        op.nside_rows(d, &vb, &ve);
+        const u64 vrows = ve - vb;          // N-side vectors this rank brings to the host
+        const u64 ncols = vrows ? N : 0;
+        res->nside_row_begin = vb;
+        res->nside_row_count = vrows;
         const bool trace = std::getenv("SVDLAS2_TRACE") != nullptr;
         const double ta0 = wall();
         double *hU = (double *)(prefetched ? fut_m.get() : host_acquire(std::max<u64>(1, d * mcols) * sizeof(double)));
         double *hV = nullptr;
         try {
-            hV = (double *)(prefetched ? fut_n.get() : host_acquire(std::max<u64>(1, d * ncols) * sizeof(double)));
+            hV = (double *)(prefetched ? fut_n.get() : host_acquire(std::max<u64>(1, vrows * ncols) * sizeof(double)));
         } catch (...) { host_release(hU); throw; }
         double *hS = (double *)std::malloc(std::max<size_t>(1, d) * sizeof(double));
         if (!hS) { host_release(hU); host_release(hV); throw Error(SVDLAS2_ERR_ALLOC, "host result allocation failed"); }
@@ -557,14 +568,14 @@ struct Solver {
         LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
         DevBuf<double> Vout; // the N-side vectors in the caller's numbering (relabelled operators only)
         if (ncols && op.relabel.active) {
-            Vout.alloc((size_t)d * N);
-            unpermute_rows(V.get(), ld, N, (u32)d, op.relabel.old2new.get(), Vout.get(), s);
+            Vout.alloc((size_t)vrows * N);
+            unpermute_rows(V.get() + vb * ld, ld, N, (u32)vrows, op.relabel.old2new.get(), Vout.get(), s);
             prof.n_kernel_launches += 1;
             LAS2_CUDA(cudaEventRecord(ev, s));
             LAS2_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
-            LAS2_CUDA(cudaMemcpyAsync(hV, Vout.get(), d * N * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
+            LAS2_CUDA(cudaMemcpyAsync(hV, Vout.get(), vrows * N * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
         } else if (ncols) {
-            LAS2_CUDA(cudaMemcpy2DAsync(hV, ncols * sizeof(double), V.get(), ld * sizeof(double), ncols * sizeof(double), d,
+            LAS2_CUDA(cudaMemcpy2DAsync(hV, ncols * sizeof(double), V.get() + vb * ld, ld * sizeof(double), ncols * sizeof(double), vrows,
                                         cudaMemcpyDeviceToHost, copy_stream));
         }
         DevBuf<double> U((size_t)d * mcols);
@@ -651,7 +662,7 @@ struct Solver {
         LAS2_CUDA(cudaStreamSynchronize(copy_stream));
         if (trace) fprintf(stderr, "[svdlas2] ritvec: waited %.3f s more for the D2H stream\n", wall() - td0);
         prof.n_host_syncs += 2;
-        prof.d2h_bytes += (d * ncols + d * mcols + d) * sizeof(double);
+        prof.d2h_bytes += (vrows * ncols + d * mcols + d) * sizeof(double);
         prof.t_download = wall() - td0; // D2H time NOT hidden behind the sigma/U kernels
         const double tf0 = wall();
         U.release(); V.release(); S.release(); nrm2.release(); Vout.release();
@@ -748,6 +759,10 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
     if (std::getenv("SVDLAS2_TRACE") && op.comm)
         fprintf(stderr, "[svdlas2] lanso: %llu purge passes, %llu reorthogonalisation sweeps split over %d ranks\n",
                 (unsigned long long)sv.prof.n_purge_passes, (unsigned long long)sv.n_sharded_sweeps, op.comm->world());
+    if (std::getenv("SVDLAS2_TRACE"))
+        fprintf(stderr, "[svdlas2] lanso: %.4f s, of which purge %.4f s (%llu passes, %llu stored vectors), analyses of T %.4f s, waiting "
+                        "for step scalars %.4f s\n", sv.prof.t_lanczos, sv.t_purge_host, (unsigned long long)sv.prof.n_purge_passes,
+                (unsigned long long)sv.prof.n_purge_vectors, sv.t_analysis_host, sv.prof.t_sync_wait);
 
     kappa = std::max(std::fabs(kappa), eps34()); // :627
     dg.kappa = kappa;

@@ -35,7 +35,14 @@ struct Operator {
     DevBuf<char> l2_flush;
     // knobs
     bool profile = false;
-    bool nside_on_rank0_only = false; // sharded runs: ranks > 0 skip the download of the replicated N-side vectors
+    int nside_mode = 0; // sharded runs, download of the replicated N-side vectors: 0 every rank, 1 rank 0 only, 2 dealt out by rows
+    // rows [b, e) of the d N-side vectors this rank brings to the host
+    void nside_rows(u64 d, u64 *b, u64 *e) const {
+        *b = 0; *e = d;
+        if (!comm) return;
+        if (nside_mode == 1 && comm->rank() != 0) *e = 0;
+        if (nside_mode == 2) { *b = d * (u64)comm->rank() / (u64)comm->world(); *e = d * (u64)(comm->rank() + 1) / (u64)comm->world(); }
+    }
     // bookkeeping
     UploadStats upload;
     double t_upload = 0.0;

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(las2):
     for n in names + declared("svdlas2_testing.h"):
         assert n in exported, f"{n} is declared in include/ but not exported by the library"
     L = _lib.lib()
-    assert L.svdlas2_abi_version() == 1
+    assert L.svdlas2_abi_version() == 2
     assert L.svdlas2_last_error() == b""
 
 

@@ -54,7 +54,8 @@ def test_sharded_solve_matches_single_gpu_and_oracle(workload, scale, dims, shar
     world = ranks_per_test()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py"),
-           "--workload", workload, "--scale", str(scale), "--dims", str(dims), "--oracle", "1"]
+           "--workload", workload, "--scale", str(scale), "--dims", str(dims), "--oracle", "1",
+           "--nside-mode", "2" if ring == "two-shot" else "0"]  # (the dealt-out download of the N-side vectors rides along)
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-3000:]
     if shard_purge_mb:
