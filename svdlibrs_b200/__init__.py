@@ -78,8 +78,8 @@ class SvdRec:
     vt: np.ndarray
     diagnostics: Diagnostics
     profile: dict = field(default_factory=dict, compare=False)
-    nside_rows: tuple = field(default=(0, 0), compare=False)  # sharded operators: (first, count) of the N-side rows held here
     trace: dict = field(default_factory=dict, compare=False)
+    nside_rows: tuple = field(default=(0, 0), compare=False)  # sharded operators: (first, count) of the N-side rows held here
 
     def recompose(self) -> np.ndarray:
         """ut' * diag(s) * vt  (src/lib.rs:2023-2028)."""
