@@ -14,7 +14,9 @@ except Exception:
 A, dims = synthetic.make(a.workload, scale=a.scale, workers=min(32, cores))
 dims = a.dims or dims
 with las2.Operator(A) as op:
+    r = None
     for i in range(a.reps):
+        r = None  # hand the previous result's pinned buffers back to the library's pool first
         t0 = time.perf_counter(); r = op.solve(dims, random_seed=12345); dt = time.perf_counter() - t0
         p = r.profile
         print(json.dumps(dict(wall=round(dt, 4), steps=r.diagnostics.lanczos_steps, d=r.d, n_opb=p["n_opb"],

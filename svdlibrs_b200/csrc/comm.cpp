@@ -119,29 +119,51 @@ void Comm::allgather_host_bytes(const void *mine, void *all, size_t bytes_each) 
     LAS2_CUDA(e);
 }
 
-void Comm::allgather_ranges(double *buf, const uint64_t *offs, cudaStream_t s) {
-    if (world_ == 1) return;
-    NcclApi &a = api();
+namespace {
+
+struct GatherPlan { uint64_t offs[9]; double *vec[8]; int world, rank, nvec; uint64_t slot; };
+
+// stage[(g * nvec + v) * slot + i] <-> vec_v[offs[g] + i]; pack: own range only; unpack: every foreign range
+__global__ void k_stage_ranges(GatherPlan p, double *__restrict__ stage, int unpack) {
+    const int g = unpack ? (int)blockIdx.y : p.rank;
+    if (unpack && g == p.rank) return;
+    const uint64_t cnt = p.offs[g + 1] - p.offs[g];
+    for (int v = 0; v < p.nvec; v++) {
+        double *vec = p.vec[v] + p.offs[g];
+        double *st = stage + ((uint64_t)g * p.nvec + v) * p.slot;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+            if (unpack) vec[i] = st[i]; else st[i] = vec[i];
+        }
+    }
+}
+
+} // namespace
+
+void Comm::allgather_ranges_n(double *const *vecs, int nvec, const uint64_t *offs, cudaStream_t s) {
+    if (world_ == 1 || nvec < 1) return;
+    if (world_ > 8 || nvec > 8) throw Error(SVDLAS2_ERR_COMM, "allgather_ranges: more than 8 ranks / vectors");
+    NcclApi &api_ = api();
     // one ncclAllGather over equal slots of a staging buffer (eight grouped broadcasts cost milliseconds on NVSwitch;
-    // one all-gather of 16 MB ~60 us), then the foreign ranges are copied to their places
-    uint64_t slot = 0;
-    for (int g = 0; g < world_; g++) slot = std::max(slot, offs[g + 1] - offs[g]);
-    if (slot == 0) return;
-    if (stage_cap_ < slot * (uint64_t)world_) {
-        if (stage_) cudaFree(stage_);
+    // one all-gather of 16 MB ~60 us); own ranges are packed and foreign ranges unpacked by one kernel each
+    GatherPlan p;
+    p.world = world_; p.rank = rank_; p.nvec = nvec; p.slot = 0;
+    for (int v = 0; v < 8; v++) p.vec[v] = v < nvec ? vecs[v] : nullptr;
+    for (int g = 0; g <= world_; g++) p.offs[g] = offs[g];
+    for (int g = 0; g < world_; g++) p.slot = std::max(p.slot, offs[g + 1] - offs[g]);
+    if (p.slot == 0) return;
+    const uint64_t per_rank = p.slot * (uint64_t)p.nvec;
+    if (stage_cap_ < per_rank * (uint64_t)world_) {
+        if (stage_) { LAS2_CUDA(cudaStreamSynchronize(s)); cudaFree(stage_); }
         stage_ = nullptr;
-        stage_cap_ = slot * (uint64_t)world_;
+        stage_cap_ = per_rank * (uint64_t)world_;
         LAS2_CUDA(cudaMalloc(&stage_, stage_cap_ * sizeof(double)));
     }
     double *st = static_cast<double *>(stage_);
-    const uint64_t own = offs[rank_ + 1] - offs[rank_];
-    if (own) LAS2_CUDA(cudaMemcpyAsync(st + rank_ * slot, buf + offs[rank_], own * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    check(a.AllGather(st + rank_ * slot, st, slot, kNcclFloat64, nccl_comm_, s), "ncclAllGather");
-    for (int g = 0; g < world_; g++) {
-        const uint64_t cnt = offs[g + 1] - offs[g];
-        if (g == rank_ || cnt == 0) continue;
-        LAS2_CUDA(cudaMemcpyAsync(buf + offs[g], st + g * slot, cnt * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    }
+    const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((p.slot + 1023) / 1024, 148));
+    k_stage_ranges<<<dim3(gx, 1), 256, 0, s>>>(p, st, 0);
+    check(api_.AllGather(st + (uint64_t)rank_ * per_rank, st, per_rank, kNcclFloat64, nccl_comm_, s), "ncclAllGather");
+    k_stage_ranges<<<dim3(gx, world_), 256, 0, s>>>(p, st, 1);
+    LAS2_LAUNCH_CHECK();
 }
 
 } // namespace las2

@@ -23,7 +23,15 @@ class Comm {
     void allreduce_sum(double *buf, uint64_t n, cudaStream_t s);
     // in-place all-gather of row ranges: rank g owns buf[offs[g] .. offs[g+1]) (offs has world()+1 entries, in doubles)
     // and every rank ends up with all of them (one ncclAllGather through an internal staging buffer)
-    void allgather_ranges(double *buf, const uint64_t *offs, cudaStream_t s);
+    void allgather_ranges(double *buf, const uint64_t *offs, cudaStream_t s) { allgather_ranges2(buf, nullptr, offs, s); }
+    // the same for a PAIR of vectors with the same row ranges (the (q, r) pair of a row-split reorthogonalisation sweep) in
+    // ONE collective: pack kernel -> ncclAllGather -> unpack kernel (b may be null)
+    void allgather_ranges2(double *a, double *b, const uint64_t *offs, cudaStream_t s) {
+        double *v[2] = {a, b};
+        allgather_ranges_n(v, b ? 2 : 1, offs, s);
+    }
+    // up to 8 vectors with the same row ranges per collective (the Ritz vectors of a row-split contraction)
+    void allgather_ranges_n(double *const *vecs, int nvec, const uint64_t *offs, cudaStream_t s);
     // host-side exchange of a few bytes per rank (set-up of the peer-memory ring): all[h * bytes_each ..] = rank h's block
     void allgather_host_bytes(const void *mine, void *all, size_t bytes_each);
 

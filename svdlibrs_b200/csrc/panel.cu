@@ -408,8 +408,7 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
         if (launches) *launches += 1;
     }
     if (shard) {
-        comm->allgather_ranges(a, offs.data(), s);
-        if (b) comm->allgather_ranges(b, offs.data(), s);
+        comm->allgather_ranges2(a, b, offs.data(), s); // the updated (q, r) pair in ONE collective
         if (b && dot_out) {
             vec_dot(a, b, ld, *dot_out, s);
             if (launches) *launches += 1;
@@ -465,7 +464,12 @@ void ritz_contract(const double *Q, u64 ld, u64 n, u32 js, const double *C, u32 
         if (launches) *launches += 1;
     }
     if (shard) {
-        for (u32 c = 0; c < d; c++) comm->allgather_ranges(V + (u64)c * ld, offs.data(), s);
+        for (u32 c = 0; c < d; c += 8) { // eight Ritz vectors per collective
+            double *v[8];
+            const int nv = (int)std::min<u32>(8, d - c);
+            for (int k = 0; k < nv; k++) v[k] = V + (u64)(c + k) * ld;
+            comm->allgather_ranges_n(v, nv, offs.data(), s);
+        }
         if (sharded) *sharded = true;
     }
 }
