@@ -374,6 +374,32 @@ def parity_block(res, fx, fx_path):
     return out
 
 
+def extra_workload(name: str, local: int, las2, peak: float, steps: int = 5, warmup: int = 3) -> dict:
+    """Resident-leg numbers of another BASELINE config (generated single-threaded: CUDA is already up, no forking here)."""
+    W = make_workload(name, 1.0, 0, 1, 1)
+    A = las2.RawMatrix(W.fmt, W.shape, W.indptr, W.indices, W.data)
+    fx, fx_path = fixture_for(name, 1.0)
+    with las2.Operator(A, device=local) as op:
+        res = None
+        for _ in range(warmup):
+            res = None
+            res = op.solve(W.dims, 0, ENDI, KAPPA, SEED)
+        t = 0.0
+        for _ in range(steps):
+            res = None
+            res = op.solve(W.dims, 0, ENDI, KAPPA, SEED)
+            t += res.profile["t_device"]
+        tm = op.time_opb(reps=20, flush_l2=24 * W.nnz <= 4 * 126e6)
+        n_opb = res.diagnostics.lanczos_steps + 1 + res.d + int(res.profile["n_restarts"])
+        ach = tm["bytes_opb"] / tm["ms_per_opb"] / 1e6
+        out = {"workload": workload_info(W)["workload"], "time_to_svd_s": t / steps, "value": n_opb * steps / t, "unit": UNIT,
+               "steps": steps, "warmup": warmup, "lanczos_steps": res.diagnostics.lanczos_steps,
+               "roofline": {"achieved": ach, "peak": peak, "frac": ach / peak, "ms_per_opb": tm["ms_per_opb"]},
+               "parity": parity_block(res, fx, fx_path)}
+        res = None
+    return out
+
+
 def run_ours(args):
     # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version banner) goes to stderr
     real_stdout = os.dup(1)
@@ -582,6 +608,13 @@ def run_ours(args):
                       "e2e_phases_s": {k: r2.profile[k] for k in ("t_upload", "t_lanczos", "t_ritvec", "t_download", "t_total")},
                       "e2e_equals_resident": bool(same)}}
 
+    # ---------------- extra: the configuration earlier rounds reported (cfg 2), resident leg only, so the series stays comparable
+    if world == 1 and not args.no_extra and W.name != "cfg2":
+        try:
+            line["extra"] = {"cfg2": extra_workload("cfg2", local, las2, peak)}
+        except Exception as e:  # never let the side measurement take the headline line down
+            line["extra"] = {"cfg2": {"error": repr(e)}}
+
     # ---------------- cpu_baseline: the oracle on this box's host cores, bounded sample (rank 0, N == 1 only)
     if world == 1 and not args.no_cpu_baseline:
         counts = reference_counts(fx, res)
@@ -610,6 +643,7 @@ def main():
                                                        "configuration the north-star targets are quoted on; it fits one B200)")
     ap.add_argument("--scale", type=float, default=1.0, help="scale every dimension (tests only; 1.0 = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg2 side measurement (N = 1 only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: fewer than 3 warm-up steps requested; the timing rules ask for >= 3")
