@@ -93,8 +93,14 @@ struct Solver {
         for (int i = 0; i < 16; i++) hs[i] = 0.0;
         {
             const char *e = std::getenv("SVDLAS2_STEP_CHAIN");
-            use_chain = (e && e[0] == '1') && step_chain_max_grid() > 0; // opt-in until validated on the GPU
-            if (use_chain) chain_work.alloc(5 * (size_t)kMaxParts);
+            // default: for vectors of up to 2 MB, where the step is launch-latency-bound (cfg 1-3); the separate kernels stream
+            // long vectors faster than one CTA per SM can (SVDLAS2_STEP_CHAIN=0 / 1 forces it off / on)
+            static const u64 max_ld = [] { const char *m = std::getenv("SVDLAS2_STEP_CHAIN_MAX_N"); return m ? (u64)std::atoll(m) : (u64)262144; }();
+            use_chain = step_chain_max_grid() > 0 && (e ? e[0] == '1' : ld <= max_ld);
+            if (use_chain) {
+                chain_work.alloc(5 * (size_t)kMaxParts + 1);
+                LAS2_CUDA(cudaMemsetAsync(chain_work.get(), 0, (5 * (size_t)kMaxParts + 1) * sizeof(double), s));
+            }
         }
         alf.assign(iters, 0.0); eta.assign(iters, 0.0); oldeta.assign(iters, 0.0);
         bet.assign(iters + 1, 0.0); ritz.assign(iters + 1, 0.0);

@@ -2,8 +2,6 @@
 // All kernels are HBM/L2-bound streams over N-vectors: 128-bit loads, grid capped at 4 CTAs per SM.
 #include "vecops.cuh"
 
-#include <cooperative_groups.h>
-
 #include <algorithm>
 
 namespace las2 {
@@ -135,11 +133,30 @@ __global__ void k_gather_scalars(GatherList g, double *__restrict__ out) {
     }
 }
 
+// Grid-wide barrier of a launch whose CTAs are all resident (grid <= number of SMs, one small CTA each): arrive on a counter,
+// the last one resets it and bumps the generation the others spin on.  (cooperative_groups' grid.sync() cost 10-40 us per
+// barrier here with 100-500 CTAs: profiles/r2_step_chain.md.)
+__device__ __forceinline__ void chain_barrier(unsigned *count, unsigned *gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned my_gen = *reinterpret_cast<volatile unsigned *>(gen);
+        if (atomicAdd(count, 1u) == gridDim.x - 1) {
+            *reinterpret_cast<volatile unsigned *>(count) = 0u;
+            __threadfence();
+            atomicAdd(gen, 1u);
+        } else {
+            while (*reinterpret_cast<volatile unsigned *>(gen) == my_gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kVecThreads)
 k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, double *__restrict__ work, double *__restrict__ host_out,
              unsigned long long seq) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+    unsigned *bar = reinterpret_cast<unsigned *>(work + 5 * (size_t)kMaxParts);
     __shared__ double sm[kVecThreads / 32];
     __shared__ double cs;
     double coef_seen[5];
@@ -168,7 +185,7 @@ k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, double *__restrict__ 
         if (threadIdx.x == 0) out[blockIdx.x] = t;
         parts = out;
         nparts = (int)gridDim.x;
-        grid.sync();
+        chain_barrier(bar, bar + 1);
     }
     const double nrm2 = cta_sum_partials(parts, nparts, &cs);
     if (c.q_next) {
@@ -215,18 +232,14 @@ void unpermute_rows(const double *V, u64 ld, u64 n, u32 d, const u32 *old2new, d
 }
 
 unsigned step_chain_max_grid() {
+    // one CTA per SM at most: every CTA of the launch is then resident at once, which the in-kernel barrier relies on
     static unsigned cached[kMaxDevicesTracked];
     static bool known[kMaxDevicesTracked];
     const int slot = current_device_slot();
     if (!known[slot]) {
-        int dev = 0, coop = 0, per_sm = 0, sms = 0;
+        int dev = 0, sms = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_chain, kVecThreads, 0) == cudaSuccess)
-            cached[slot] = (unsigned)std::min(kMaxParts, per_sm * sms);
-        else
-            cached[slot] = 0;
+        cached[slot] = (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) ? (unsigned)sms : 0u;
         cudaGetLastError();
         known[slot] = true;
     }
@@ -236,11 +249,9 @@ unsigned step_chain_max_grid() {
 void vec_step_chain(double *r, u64 ld, const StepChain &c, double *work, double *host_out, unsigned long long seq, cudaStream_t s) {
     u64 n2 = ld / 2;
     unsigned grid = std::min<unsigned>(step_chain_max_grid(), vec_grid(ld));
-    if (grid == 0) throw Error(SVDLAS2_ERR_CUDA, "cooperative launch unavailable");
-    StepChain cc = c;
-    double2 *r2 = reinterpret_cast<double2 *>(r);
-    void *args[] = {&r2, &n2, &cc, &work, &host_out, &seq};
-    LAS2_CUDA(cudaLaunchCooperativeKernel((const void *)k_step_chain, dim3(grid), dim3(kVecThreads), args, 0, s));
+    if (grid == 0) throw Error(SVDLAS2_ERR_CUDA, "step chain: no device");
+    k_step_chain<<<grid, kVecThreads, 0, s>>>(reinterpret_cast<double2 *>(r), n2, c, work, host_out, seq);
+    LAS2_LAUNCH_CHECK();
 }
 
 unsigned vec_grid(u64 ld) {

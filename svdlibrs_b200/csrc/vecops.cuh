@@ -46,7 +46,7 @@ void vec_axpy_dot(double *r, const double *x, Coef coef, const double *y, u64 ld
 // r -= coef * x                                       (svd_daxpy, :840-844)
 void vec_axpy(double *r, const double *x, Coef coef, u64 ld, cudaStream_t s);
 
-// The local re-orthogonalisation chain of one Lanczos step (reference src/lib.rs:1279-1304) as ONE cooperative launch:
+// The local re-orthogonalisation chain of one Lanczos step (reference src/lib.rs:1279-1304) as ONE launch:
 //   phase k:  c_k = canonical sum of the previous phase's partials (phase 0: the alf partials of the opb epilogue) ;
 //             r -= c_k * x_k ;  partials of  r . y_k   (y_k == nullptr: r . r)
 // with a grid-wide barrier between the phases, instead of 3-5 dependent launches of k_axpy_dot plus k_gather_scalars.  The
@@ -62,7 +62,8 @@ struct StepChain {
     int alf_nparts;
     double *q_next;           // may be nullptr
 };
-// work: 5 * kMaxParts doubles of partial scratch + 2 unsigned ints; host_out: 4 doubles + 1 sequence word (pinned).
+// work: 5 * kMaxParts doubles of partial scratch + 2 unsigned ints (ZEROED once by the caller: the launch's grid barrier);
+// host_out: 4 doubles + 1 sequence word (pinned).  The grid is at most one CTA per SM.
 void vec_step_chain(double *r, u64 ld, const StepChain &c, double *work, double *host_out, unsigned long long seq, cudaStream_t s);
 unsigned step_chain_max_grid(); // co-resident CTAs of the chain kernel on the current device (0: cooperative launch unavailable)
 
