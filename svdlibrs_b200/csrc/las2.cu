@@ -93,13 +93,13 @@ struct Solver {
         for (int i = 0; i < 16; i++) hs[i] = 0.0;
         {
             const char *e = std::getenv("SVDLAS2_STEP_CHAIN");
-            // default: for vectors of up to 2 MB, where the step is launch-latency-bound (cfg 1-3); the separate kernels stream
-            // long vectors faster than one CTA per SM can (SVDLAS2_STEP_CHAIN=0 / 1 forces it off / on)
-            static const u64 max_ld = [] { const char *m = std::getenv("SVDLAS2_STEP_CHAIN_MAX_N"); return m ? (u64)std::atoll(m) : (u64)262144; }();
+            // default: for vectors of up to 8 MB, where the step is launch-latency-bound (cfg 1-3, cfg 5); the separate kernels
+            // stream longer vectors faster than one CTA per SM can (SVDLAS2_STEP_CHAIN=0 / 1 forces it off / on)
+            static const u64 max_ld = [] { const char *m = std::getenv("SVDLAS2_STEP_CHAIN_MAX_N"); return m ? (u64)std::atoll(m) : (u64)1 << 20; }();
             use_chain = step_chain_max_grid() > 0 && (e ? e[0] == '1' : ld <= max_ld);
             if (use_chain) {
-                chain_work.alloc(5 * (size_t)kMaxParts + 1);
-                LAS2_CUDA(cudaMemsetAsync(chain_work.get(), 0, (5 * (size_t)kMaxParts + 1) * sizeof(double), s));
+                chain_work.alloc(6 * (size_t)kMaxParts + 1);
+                LAS2_CUDA(cudaMemsetAsync(chain_work.get(), 0, (6 * (size_t)kMaxParts + 1) * sizeof(double), s));
             }
         }
         alf.assign(iters, 0.0); eta.assign(iters, 0.0); oldeta.assign(iters, 0.0);
@@ -193,6 +193,8 @@ struct Solver {
     void wait_chain(double *out) {
         volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(hs.get() + 4);
         const double tw0 = wall();
+        static const bool poll = [] { const char *e = std::getenv("SVDLAS2_CHAIN_POLL"); return !(e && e[0] == '0'); }();
+        if (!poll) LAS2_CUDA(cudaStreamSynchronize(s)); // experiment knob: plain stream sync instead of polling the flag
         u64 spins = 0;
         while (*flag != chain_seq) {
             if ((++spins & 0xfff) == 0) {
@@ -338,7 +340,10 @@ struct Solver {
             // r = B'B q_j - rnm q_{j-1} ; alf = r . q_j  (sharded: the all-reduce, the update and the dot are ONE kernel)
             // (slot 7 is reserved for alf: in a sharded run it points into the ring's partial buffer)
             constexpr int s_alf = 7;
-            opb_step(q(j), q(j - 1), rn, slot[s_alf]);
+            const bool chain_now = use_chain && j > kMaxLL;
+            const bool fold_epilogue = chain_now && !op.ring; // single GPU: the update r -= rnm q_{j-1} becomes the chain's first phase
+            if (fold_epilogue) opb(q(j), r.get());
+            else opb_step(q(j), q(j - 1), rn, slot[s_alf]);
             if (j <= kMaxLL) {
                 // |alf[j-1]| > 4 |alf[j]| decides ll only while j <= MAXLL (:1282): needs alf[j] now
                 double a;
@@ -347,25 +352,30 @@ struct Solver {
             }
             double v[4];
             const u64 purges_before = prof.n_purge_fired;
-            if (use_chain && j > kMaxLL) {
-                // ---- :1279-1304 as ONE cooperative launch (vec_step_chain), scalars through pinned memory ----
+            if (chain_now) {
+                // ---- :1277-1304 as ONE launch (vec_step_chain), scalars through pinned memory ----
                 const u64 lim = std::min<u64>(j - 1, *ll);
-                const bool speculate = j + 1 < last;
+                static const bool spec_on = [] { const char *e = std::getenv("SVDLAS2_CHAIN_SPEC"); return !(e && e[0] == '0'); }();
+                const bool speculate = spec_on && j + 1 < last;
                 if (speculate) ensure_cols(j + 2);
                 StepChain c;
-                c.nphases = (int)lim + 3;
-                c.x[0] = q(j);
-                c.y[0] = lim > 0 ? q(0) : q(j - 1);
+                const int o = fold_epilogue ? 1 : 0; // phases shift by one when the epilogue leads the chain
+                c.nphases = (int)lim + 3 + o;
+                if (fold_epilogue) { c.x[0] = q(j - 1); c.y[0] = q(j); } // r -= rnm q_{j-1} ; alf = r . q_j
+                c.x[o] = q(j);
+                c.y[o] = lim > 0 ? q(0) : q(j - 1);
                 for (u64 i = 1; i <= lim; i++) {
-                    c.x[i] = q(i - 1);
-                    c.y[i] = i < lim ? q(i) : q(j - 1);
+                    c.x[o + i] = q(i - 1);
+                    c.y[o + i] = i < lim ? q(i) : q(j - 1);
                     eta[i - 1] = eps1;
                     oldeta[i - 1] = eps1;
                 }
-                c.x[lim + 1] = q(j - 1); c.y[lim + 1] = q(j);
-                c.x[lim + 2] = q(j);     c.y[lim + 2] = nullptr;
-                c.pick[0] = 0; c.pick[1] = (int)lim + 1; c.pick[2] = (int)lim + 2; c.pick[3] = 0;
-                c.alf_parts = slot[s_alf].parts; c.alf_nparts = slot[s_alf].nparts;
+                c.x[o + lim + 1] = q(j - 1); c.y[o + lim + 1] = q(j);
+                c.x[o + lim + 2] = q(j);     c.y[o + lim + 2] = nullptr;
+                c.pick[0] = o; c.pick[1] = o + (int)lim + 1; c.pick[2] = o + (int)lim + 2; c.pick[3] = 0;
+                c.alf_parts = fold_epilogue ? nullptr : slot[s_alf].parts;
+                c.alf_nparts = fold_epilogue ? 0 : slot[s_alf].nparts;
+                c.coef0 = rn;
                 c.q_next = speculate ? q(j + 1) : nullptr;
                 chain_seq += 1;
                 vec_step_chain(r.get(), ld, c, chain_work.get(), hs.get(), chain_seq, s);

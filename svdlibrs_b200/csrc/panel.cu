@@ -65,19 +65,39 @@ k_panel_dots(const double *__restrict__ Q, u64 ld, u32 col0, u32 ncols, const do
     }
 }
 
-// coeffs[rhs * ncols + c] = sum over row blocks (in order) ; abs_parts[blockIdx.x * 2 + rhs] = sum |coeff| of the CTA's columns
+// coeffs[rhs * ncols + c] = sum over row blocks ; abs_parts[blockIdx.x * 2 + rhs] = sum |coeff| of the CTA's columns.
+// A CTA of 128 x 8 threads owns 128 columns; the row blocks are cut into 8 contiguous ranges (one per threadIdx.y), each summed
+// in order, and the 8 range sums are added in range order: a fixed order, and an eighth of the dependent-add chain (977 row
+// blocks at cfg 4: 185 us per sweep with one thread per column).
+constexpr int kReduceSplit = 8;
 template <int NRHS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128 * kReduceSplit)
 k_panel_reduce(const double *__restrict__ partials, u32 nblocks, u32 ncols, double *__restrict__ coeffs,
                double *__restrict__ abs_a, double *__restrict__ abs_b) {
     __shared__ double sm[2][4];
+    __shared__ double part[kReduceSplit][NRHS][128];
     const u32 c = blockIdx.x * 128 + threadIdx.x;
     double ca = 0.0, cb = 0.0;
+    {
+        const u32 lo = (u32)((u64)nblocks * threadIdx.y / kReduceSplit), hi = (u32)((u64)nblocks * (threadIdx.y + 1) / kReduceSplit);
+        double pa = 0.0, pb = 0.0;
+        if (c < ncols) {
+            for (u32 rb = lo; rb < hi; rb++) {
+                const double *p = partials + ((u64)rb * ncols + c) * NRHS;
+                pa += p[0];
+                if (NRHS > 1) pb += p[1];
+            }
+        }
+        part[threadIdx.y][0][threadIdx.x] = pa;
+        if (NRHS > 1) part[threadIdx.y][NRHS - 1][threadIdx.x] = pb;
+    }
+    __syncthreads();
+    if (threadIdx.y != 0) return;
     if (c < ncols) {
-        for (u32 rb = 0; rb < nblocks; rb++) {
-            const double *p = partials + ((u64)rb * ncols + c) * NRHS;
-            ca += p[0];
-            if (NRHS > 1) cb += p[1];
+#pragma unroll
+        for (int k = 0; k < kReduceSplit; k++) {
+            ca += part[k][0][threadIdx.x];
+            if (NRHS > 1) cb += part[k][NRHS - 1][threadIdx.x];
         }
         coeffs[c] = ca;
         if (NRHS > 1) coeffs[ncols + c] = cb;
@@ -85,7 +105,8 @@ k_panel_reduce(const double *__restrict__ partials, u32 nblocks, u32 ncols, doub
     double va = warp_sum(fabs(ca)), vb = warp_sum(fabs(cb));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { sm[0][warp] = va; sm[1][warp] = vb; }
-    __syncthreads();
+    // (only the 128 threads of threadIdx.y == 0 are left: a named barrier over exactly them)
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     if (threadIdx.x == 0) {
         abs_a[blockIdx.x] = ((sm[0][0] + sm[0][1]) + sm[0][2]) + sm[0][3];
         abs_b[blockIdx.x] = ((sm[1][0] + sm[1][1]) + sm[1][2]) + sm[1][3];
@@ -367,10 +388,10 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
     // ---- coefficients ----
     if (b) {
         k_panel_dots<2><<<grid, kPanelThreads, 0, s>>>(Q, ld, col0, ncols, a, b, work.partials, rb0);
-        k_panel_reduce<2><<<nred, 128, 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
+        k_panel_reduce<2><<<nred, dim3(128, kReduceSplit), 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
     } else {
         k_panel_dots<1><<<grid, kPanelThreads, 0, s>>>(Q, ld, col0, ncols, a, nullptr, work.partials, rb0);
-        k_panel_reduce<1><<<nred, 128, 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
+        k_panel_reduce<1><<<nred, dim3(128, kReduceSplit), 0, s>>>(work.partials, nblocks, ncols, work.coeffs, abs_a->parts, abs_b->parts);
     }
     if (launches) *launches += 2;
     if (shard) {

@@ -153,17 +153,17 @@ __device__ __forceinline__ void chain_barrier(unsigned *count, unsigned *gen) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kVecThreads)
+__global__ void __launch_bounds__(1024)
 k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, double *__restrict__ work, double *__restrict__ host_out,
              unsigned long long seq) {
-    unsigned *bar = reinterpret_cast<unsigned *>(work + 5 * (size_t)kMaxParts);
-    __shared__ double sm[kVecThreads / 32];
+    unsigned *bar = reinterpret_cast<unsigned *>(work + 6 * (size_t)kMaxParts);
+    __shared__ double sm[32];
     __shared__ double cs;
-    double coef_seen[5];
+    double coef_seen[6];
     const double *parts = c.alf_parts;
     int nparts = c.alf_nparts;
     for (int k = 0; k < c.nphases; k++) {
-        const double coef = cta_sum_partials(parts, nparts, &cs);
+        const double coef = (k == 0 && parts == nullptr) ? c.coef0 : cta_sum_partials(parts, nparts, &cs);
         coef_seen[k] = coef;
         const double nc = -coef;
         const double2 *__restrict__ x = reinterpret_cast<const double2 *>(c.x[k]);
@@ -250,7 +250,9 @@ void vec_step_chain(double *r, u64 ld, const StepChain &c, double *work, double 
     u64 n2 = ld / 2;
     unsigned grid = std::min<unsigned>(step_chain_max_grid(), vec_grid(ld));
     if (grid == 0) throw Error(SVDLAS2_ERR_CUDA, "step chain: no device");
-    k_step_chain<<<grid, kVecThreads, 0, s>>>(reinterpret_cast<double2 *>(r), n2, c, work, host_out, seq);
+    // one CTA per SM at most (the in-kernel barrier): long vectors get 1024 threads per CTA to keep enough loads in flight
+    const unsigned threads = n2 > (u64)grid * kVecThreads * 2 ? 1024u : (unsigned)kVecThreads;
+    k_step_chain<<<grid, threads, 0, s>>>(reinterpret_cast<double2 *>(r), n2, c, work, host_out, seq);
     LAS2_LAUNCH_CHECK();
 }
 

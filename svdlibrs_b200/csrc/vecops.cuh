@@ -54,15 +54,16 @@ void vec_axpy(double *r, const double *x, Coef coef, u64 ld, cudaStream_t s);
 // memory, followed by a sequence number the host polls: no cudaStreamSynchronize per step.  Optionally also writes the next
 // Lanczos vector q_next = r / sqrt(|r|^2) (the host discards it when purge / a restart changes r).
 struct StepChain {
-    int nphases;              // 3 .. 5
-    const double *x[5];       // axpy vectors
-    const double *y[5];       // dot vectors (nullptr: the norm)
+    int nphases;              // 3 .. 6
+    const double *x[6];       // axpy vectors
+    const double *y[6];       // dot vectors (nullptr: the norm)
     int pick[4];              // which phase's coefficient goes to out[0], out[1], out[2]; out[3] is always the final norm^2
-    const double *alf_parts;  // partials of the coefficient of phase 0
-    int alf_nparts;
+    const double *alf_parts;  // partials of the coefficient of phase 0 (nullptr: the coefficient is coef0, known on the host --
+    int alf_nparts;           // the opb epilogue r -= rnm q_{j-1} folded into the chain as its first phase)
+    double coef0;
     double *q_next;           // may be nullptr
 };
-// work: 5 * kMaxParts doubles of partial scratch + 2 unsigned ints (ZEROED once by the caller: the launch's grid barrier);
+// work: 6 * kMaxParts doubles of partial scratch + 2 unsigned ints (ZEROED once by the caller: the launch's grid barrier);
 // host_out: 4 doubles + 1 sequence word (pinned).  The grid is at most one CTA per SM.
 void vec_step_chain(double *r, u64 ld, const StepChain &c, double *work, double *host_out, unsigned long long seq, cudaStream_t s);
 unsigned step_chain_max_grid(); // co-resident CTAs of the chain kernel on the current device (0: cooperative launch unavailable)
