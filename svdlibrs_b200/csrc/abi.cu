@@ -166,6 +166,13 @@ void svdlas2_operator_destroy(svdlas2_operator *op_) {
     if (!op) return;
     cudaSetDevice(op->device);
     if (op->stream) cudaStreamSynchronize(op->stream);
+    if (op->ring && op->comm) {
+        // a sharded operator is destroyed collectively: every rank un-maps the peers' ring blocks, then (after a barrier)
+        // frees its own -- an exporter must not free memory another process still has open
+        op->ring->close_peers();
+        try { op->comm->barrier(); } catch (...) {}
+        op->ring.reset();
+    }
     delete op;
 }
 

@@ -91,8 +91,19 @@ Comm *Comm::create(int rank, int world, const uint8_t *id_bytes) {
     return c;
 }
 
+void Comm::barrier() {
+    if (world_ == 1 || !nccl_comm_) return;
+    unsigned char mine = 1, all[8 * 8] = {0};
+    allgather_host_bytes(&mine, all, 1);
+}
+
 Comm::~Comm() {
-    delete small_;
+    if (small_) {
+        // every rank un-maps the others' blocks before anybody frees its own
+        small_->close_peers();
+        try { barrier(); } catch (...) {}
+        delete small_;
+    }
     if (stage_) cudaFree(stage_);
     if (nccl_comm_) api().CommDestroy(nccl_comm_);
 }

@@ -34,6 +34,8 @@ class Comm {
     void allgather_ranges_n(double *const *vecs, int nvec, const uint64_t *offs, cudaStream_t s);
     // host-side exchange of a few bytes per rank (set-up of the peer-memory ring): all[h * bytes_each ..] = rank h's block
     void allgather_host_bytes(const void *mine, void *all, size_t bytes_each);
+    // all ranks have reached this point (NCCL; blocks the host)
+    void barrier();
 
   private:
     Comm() = default;

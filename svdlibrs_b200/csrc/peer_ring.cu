@@ -222,9 +222,13 @@ PeerRing *PeerRing::create(Comm *comm, u64 n_doubles) {
     return R.release();
 }
 
-PeerRing::~PeerRing() {
+void PeerRing::close_peers() {
     for (int h = 0; h < G; h++)
-        if (h != g && peer_base[h]) cudaIpcCloseMemHandle(peer_base[h]);
+        if (h != g && peer_base[h]) { cudaIpcCloseMemHandle(peer_base[h]); peer_base[h] = nullptr; }
+}
+
+PeerRing::~PeerRing() {
+    close_peers();
     if (base) cudaFree(base);
 }
 

@@ -42,6 +42,9 @@ struct PeerRing {
     u64 calls = 0, two_shot_calls = 0;
 
     ~PeerRing();
+    // un-map the peers' blocks (idempotent).  Owners do: close_peers() on every rank, a barrier, THEN destroy the ring --
+    // an exporter must not free its block while another process still has it open
+    void close_peers();
     // collective: every rank of `comm` calls it with the same n.  Throws Error(SVDLAS2_ERR_COMM) when peer memory is not
     // available between the ranks (the caller then stays on the NCCL path).
     static PeerRing *create(Comm *comm, u64 n_doubles);
