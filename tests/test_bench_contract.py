@@ -32,3 +32,22 @@ def test_reference_arm_line():
 def test_reference_arm_other_ranks_exit_quietly():
     out = run_bench("--gpus", "2", env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out == [] or out == [""]
+
+
+def test_reference_arm_extrapolated_sample():
+    """Workloads with a recorded full-size oracle run (tests/golden/oracle_<cfg>.json) use the SURVEY 8(d) sample: a few real
+    svd_opb, one purge sweep, the BLAS-1 chain, contraction terms and imtql2 at the final js, multiplied by the counts of
+    the oracle's full solve; the line says so in a structured `sample_detail`."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = p.stdout.strip().splitlines()
+    assert len(out) == 1
+    d = json.loads(out[0])
+    assert d["impl"] == "reference" and d["config"]["name"] == "cfg1" and d["value"] > 0
+    sd = d["cpu_baseline"]["sample_detail"]
+    assert sd["kind"] == "extrapolated" and sd["counts"]["lanczos_steps"] == 782 and sd["opb_timed_total"] >= 10
+    assert sd["fixture"].endswith("oracle_cfg1.json") and sd["full_run_on_build_box_s"] > 0
+    # the extrapolation reproduces the measured full run of the same box to within a factor of two
+    assert 0.5 < d["time_to_svd_s"]["extrapolated"] / sd["full_run_on_build_box_s"] < 2.0
+    assert d["e2e"] == {"value": d["value"], "unit": "opb/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
