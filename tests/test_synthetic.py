@@ -45,3 +45,24 @@ def test_parallel_generation_is_bit_identical():
 def test_oracle_unit_costs_are_positive(oracle):
     u = oracle.unit_costs(50_000, 4)
     assert all(v > 0 for v in u.values())
+
+
+def test_bench_workload_shards_tile_the_matrix():
+    """bench.py at N > 1: every rank generates only its rows of the oriented operator; together they are the N = 1 matrix
+    (tall CSR configs directly, the wide CSC config through its tall transpose)."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name, scale in (("cfg2", 0.01), ("cfg3", 0.005), ("cfg1", 0.2)):
+        full = bench.make_workload(name, scale, 0, 1, 1)
+        parts = [bench.make_workload(name, scale, r, 3, 1) for r in range(3)]
+        assert [p.row_begin for p in parts] == sorted(p.row_begin for p in parts) and parts[0].row_begin == 0
+        assert sum(p.local_shape[0] for p in parts) == parts[0].m_global
+        assert sum(p.local_nnz for p in parts) == full.local_nnz
+        assert all(p.transposed == full.transposed for p in parts)
+        if full.fmt in ("csr", "csc") and (name != "cfg1"):
+            # power-law configs: the concatenated shards ARE the arrays of the full matrix (CSR of B = the CSC arrays of cfg 3)
+            assert np.array_equal(np.concatenate([p.indices for p in parts]), full.indices)
+            assert np.array_equal(np.concatenate([p.data for p in parts]), full.data)
