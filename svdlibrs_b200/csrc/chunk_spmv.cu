@@ -247,6 +247,29 @@ k_slab_reduce(const u32 *__restrict__ slot, const double *__restrict__ part, u64
     }
 }
 
+// The same for a FEW slabs (the wide-slab streams: 2..16 blocks of 2^20 columns): one thread per row adds the row's pieces in
+// ascending slab order; the slot loads of a warp are one 128-byte line per slab and the partials it then fetches are nearly
+// consecutive.  (k_slab_reduce spends eight warps and a shared-memory combine per 32 rows, which is what 610 slabs need and
+// what made it instruction-bound at 10 slabs: 0.16 ms per SpMV at cfg 4, profiles/r2g_ncu_summary.md.)
+constexpr int kFewSlabs = 16;
+__global__ void __launch_bounds__(256)
+k_slab_reduce_few(const u32 *__restrict__ slot, const double *__restrict__ part, u64 rows, u32 nslabs, double *__restrict__ y) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r < rows;
+    u32 id[kFewSlabs];
+#pragma unroll
+    for (int b = 0; b < kFewSlabs; b++) id[b] = (live && (u32)b < nslabs) ? slot[(u64)b * rows + r] : kNoPiece;
+    cudaGridDependencySynchronize();
+    double p[kFewSlabs];
+#pragma unroll
+    for (int b = 0; b < kFewSlabs; b++) p[b] = id[b] != kNoPiece ? part[id[b]] : 0.0;
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < kFewSlabs; b++) s += p[b];
+    if (live) y[r] = s;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 
 __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
@@ -1064,8 +1087,12 @@ void run_stream(const DeviceCsr &A, const ChunkStream &K, const double *x, doubl
                (const double *)K.carry, (const double *)K.head, out, K.num_chunks);
     if (launches) *launches += 2;
     if (K.slabs) {
-        launch_pdl(pdl, k_slab_reduce, dim3(cdiv(K.rows, 32)), dim3(kReduceWarps * 32), 0, s, (const u32 *)K.piece_id,
-                   (const double *)K.part, (u64)K.rows, K.nslabs, y);
+        if (K.nslabs <= (u32)kFewSlabs)
+            launch_pdl(pdl, k_slab_reduce_few, dim3(cdiv(K.rows, 256)), dim3(256), 0, s, (const u32 *)K.piece_id,
+                       (const double *)K.part, (u64)K.rows, K.nslabs, y);
+        else
+            launch_pdl(pdl, k_slab_reduce, dim3(cdiv(K.rows, 32)), dim3(kReduceWarps * 32), 0, s, (const u32 *)K.piece_id,
+                       (const double *)K.part, (u64)K.rows, K.nslabs, y);
         if (launches) *launches += 1;
     }
     LAS2_LAUNCH_CHECK();
