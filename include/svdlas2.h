@@ -162,7 +162,6 @@ enum { SVDLAS2_FMT_CSR = 0, SVDLAS2_FMT_CSC = 1, SVDLAS2_FMT_COO = 2 };
  * Orientation (src/lib.rs:606) is decided here: B = A, or A' when ncols >= 1.2*nrows. */
 SVDLAS2_API int svdlas2_operator_create(int format, uint64_t nrows, uint64_t ncols, uint64_t nnz, const uint64_t *a,
                             const uint64_t *b, const double *values, int device, svdlas2_operator **op);
-/* (a sharded operator that exchanges over peer memory is destroyed COLLECTIVELY: every rank must call this, like the create) */
 SVDLAS2_API void svdlas2_operator_destroy(svdlas2_operator *op);
 
 /* svdLAS2 (src/lib.rs:570-655) on a resident operator.  random_seed == 0 draws a seed from OS entropy like the

@@ -166,14 +166,7 @@ void svdlas2_operator_destroy(svdlas2_operator *op_) {
     if (!op) return;
     cudaSetDevice(op->device);
     if (op->stream) cudaStreamSynchronize(op->stream);
-    if (op->ring && op->comm) {
-        // a sharded operator is destroyed collectively: every rank un-maps the peers' ring blocks, then (after a barrier)
-        // frees its own -- an exporter must not free memory another process still has open
-        op->ring->close_peers();
-        try { op->comm->barrier(); } catch (...) {}
-        op->ring.reset();
-    }
-    delete op;
+    delete op; // (the peer-memory ring belongs to the communicator)
 }
 
 int svdlas2_operator_solve(svdlas2_operator *op_, uint64_t dimensions, uint64_t iterations, const double end_interval[2],
@@ -479,7 +472,7 @@ int svdlas2_test_ring_emulation(int G, uint64_t n, const double *ys, const doubl
 int svdlas2_operator_info(const svdlas2_operator *op_, const char *key, double *value) {
     const Operator *op = reinterpret_cast<const Operator *>(op_);
     if (!op || !key || !value) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
-    const PeerRing *R = op->ring.get();
+    const PeerRing *R = op->ring;
     const u64 ld = (op->N + 31) / 32 * 32;
     if (!std::strcmp(key, "relabelled")) { *value = op->relabel.active ? 1.0 : 0.0; return SVDLAS2_OK; }
     if (!std::strcmp(key, "ring")) { *value = R ? 1.0 : 0.0; return SVDLAS2_OK; }
@@ -563,14 +556,11 @@ int svdlas2_operator_create_shard(uint64_t m_global, uint64_t n, uint64_t row_be
         op->comm = (c && c->world() > 1) ? c : nullptr;
         build_operator_from_csr(op->M, n, local_nnz, local_offsets, local_indices, values, op->stream, op->B, op->BT,
                                 op->upload, op->relabel, op->comm);
-        const char *ring_env = std::getenv("SVDLAS2_RING");
-        if (op->comm && !(ring_env && ring_env[0] == '0')) {
-            // collective; every rank reaches the same verdict.  Without peer memory the exchange stays on ncclAllReduce.
-            try { op->ring.reset(PeerRing::create(op->comm, (n + 31) / 32 * 32)); }
-            catch (const Error &e) {
-                op->ring.reset();
-                if (std::getenv("SVDLAS2_TRACE")) fprintf(stderr, "[svdlas2] %s -- using ncclAllReduce\n", e.what());
-            }
+        // collective; every rank reaches the same verdict.  Without peer memory the exchange stays on ncclAllReduce.
+        if (op->comm) op->ring = op->comm->vector_ring((n + 31) / 32 * 32);
+        if (op->ring) {
+            op->ring->reset_vectors(op->stream);
+            LAS2_CUDA(cudaStreamSynchronize(op->stream));
         }
         op->t_upload = wall_now() - t0;
         *out = reinterpret_cast<svdlas2_operator *>(op.release());

@@ -97,7 +97,32 @@ void Comm::barrier() {
     allgather_host_bytes(&mine, all, 1);
 }
 
+PeerRing *Comm::vector_ring(uint64_t n_doubles) {
+    if (world_ == 1 || ring_unavailable_) return nullptr;
+    const char *ring_env = std::getenv("SVDLAS2_RING");
+    if (ring_env && ring_env[0] == '0') return nullptr;
+    if (big_ && big_->cap >= n_doubles) return big_;
+    if (big_) { // grow: every rank un-maps the old blocks before anybody frees its own
+        big_->close_peers();
+        barrier();
+        delete big_;
+        big_ = nullptr;
+    }
+    try { big_ = PeerRing::create(this, n_doubles); }
+    catch (const Error &e) {
+        big_ = nullptr;
+        ring_unavailable_ = true; // same verdict on every rank (PeerRing::create agrees on it collectively)
+        if (std::getenv("SVDLAS2_TRACE")) fprintf(stderr, "[svdlas2] %s -- using ncclAllReduce\n", e.what());
+    }
+    return big_;
+}
+
 Comm::~Comm() {
+    if (big_) {
+        big_->close_peers();
+        try { barrier(); } catch (...) {}
+        delete big_;
+    }
     if (small_) {
         // every rank un-maps the others' blocks before anybody frees its own
         small_->close_peers();

@@ -36,6 +36,9 @@ class Comm {
     void allgather_host_bytes(const void *mine, void *all, size_t bytes_each);
     // all ranks have reached this point (NCCL; blocks the host)
     void barrier();
+    // the peer-memory ring for vectors of n doubles (collective: every rank calls it with the same n).  One ring per
+    // communicator, grown when a longer vector comes along; nullptr when peer memory is unavailable or SVDLAS2_RING=0.
+    PeerRing *vector_ring(uint64_t n_doubles);
 
   private:
     Comm() = default;
@@ -44,6 +47,8 @@ class Comm {
     // short sums (reorthogonalisation coefficients, squared norms, the shared seed) go through a peer-memory ring that adds
     // in rank order (peer_ring.cuh) when peer memory is available: no floating-point result then depends on NCCL's choices
     PeerRing *small_ = nullptr;
+    PeerRing *big_ = nullptr;   // the operators' vector ring (vector_ring())
+    bool ring_unavailable_ = false;
     void *stage_ = nullptr; // all-gather staging (world * largest range doubles)
     uint64_t stage_cap_ = 0;
 };

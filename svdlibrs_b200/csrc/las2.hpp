@@ -28,8 +28,10 @@ struct Operator {
     Relabel relabel;  // N-side ids re-assigned at upload (device_csr.cuh); vectors inside the solver are in the NEW order
     Comm *comm = nullptr; // borrowed; null on a single GPU
     // the exchange step of a sharded opb over NVLink peer memory, fused with the first update of the Lanczos step
-    // (peer_ring.cuh); null on a single GPU, when peer memory cannot be mapped, or with SVDLAS2_RING=0 (then: ncclAllReduce)
-    std::unique_ptr<PeerRing> ring;
+    // (peer_ring.cuh); null on a single GPU, when peer memory cannot be mapped, or with SVDLAS2_RING=0 (then: ncclAllReduce).
+    // Borrowed from the communicator, which keeps ONE ring for all the operators it serves (mapping peer memory costs far
+    // more than an upload of a small shard; an operator created per call must not pay it every time).
+    PeerRing *ring = nullptr;
     // scratch for opa/opb/time_opb
     DevBuf<double> tmp_m, tmp_x, tmp_y;
     DevBuf<char> l2_flush;

@@ -222,6 +222,13 @@ PeerRing *PeerRing::create(Comm *comm, u64 n_doubles) {
     return R.release();
 }
 
+void PeerRing::reset_vectors(cudaStream_t s) {
+    if (!cap) return;
+    LAS2_CUDA(cudaMemsetAsync(y[0][g], 0, cap * sizeof(double), s));
+    LAS2_CUDA(cudaMemsetAsync(y[1][g], 0, cap * sizeof(double), s));
+    LAS2_CUDA(cudaMemsetAsync(r[g], 0, cap * sizeof(double), s));
+}
+
 void PeerRing::close_peers() {
     for (int h = 0; h < G; h++)
         if (h != g && peer_base[h]) { cudaIpcCloseMemHandle(peer_base[h]); peer_base[h] = nullptr; }

@@ -45,6 +45,8 @@ struct PeerRing {
     // un-map the peers' blocks (idempotent).  Owners do: close_peers() on every rank, a barrier, THEN destroy the ring --
     // an exporter must not free its block while another process still has it open
     void close_peers();
+    // zero this rank's vector buffers (a new operator attaches: the padding beyond its N must read 0.0)
+    void reset_vectors(cudaStream_t s);
     // collective: every rank of `comm` calls it with the same n.  Throws Error(SVDLAS2_ERR_COMM) when peer memory is not
     // available between the ranks (the caller then stays on the NCCL path).
     static PeerRing *create(Comm *comm, u64 n_doubles);
