@@ -387,13 +387,12 @@ struct Solver {
             const double *ax = q(j);
             int prev = s_alf;
             const u64 lim = std::min<u64>(j - 1, *ll);
-            int s_ll[2] = {-1, -1};
             for (u64 i = 0; i < lim; i++) {
                 vec_axpy_dot(r.get(), ax, sum_of(prev), q(i), ld, slot[ns], s);
                 prof.n_kernel_launches += 1;
                 ax = q(i);
                 prev = ns;
-                s_ll[i] = ns++;
+                ns++;
                 eta[i] = eps1;
                 oldeta[i] = eps1;
             }
@@ -405,7 +404,6 @@ struct Solver {
             vec_axpy_dot(r.get(), q(j), sum_of(s_t2), nullptr, ld, slot[ns], s); // r -= t2 q_j ; |r|^2
             const int s_nrm = ns++;
             prof.n_kernel_launches += 3;
-            (void)s_ll;
             gather({s_alf, s_t1, s_t2, s_nrm}, v); // the one read-back of this step
             }
             const double nrm2 = v[3];
