@@ -27,6 +27,10 @@ SVDLAS2_API int svdlas2_test_refine_bounds(int *enough, double endl, double endr
                                            uint64_t step, double tol, uint64_t *neig);
 /* insert_sort (src/lib.rs:815-825) */
 SVDLAS2_API void svdlas2_test_cosort(uint64_t n, double *keys, double *vals);
+/* Host result pool (host_pool.cpp): acquires a block of `bytes`, writes its first and last byte, releases it and trims the
+ * cache.  *node receives the memory node the block was steered to (the node of the current CUDA device; -1 when there is no
+ * device or the topology is not exposed).  Works without a GPU (the block is then pageable).  Returns a status code. */
+SVDLAS2_API int svdlas2_test_host_block(uint64_t bytes, int *node);
 /* GPU tuning hook (needs a device): device-times `reps` reorthogonalisation passes of purge (src/lib.rs:1372-1388) of a
  * pair (q, r) against `ncols` synthetic Lanczos vectors of length n; outputs milliseconds per pass spent in the
  * coefficient kernels (c = Q'[q r]) and in the update kernel ([q r] -= Q c).  Returns a status code. */

@@ -5,7 +5,9 @@
 // cudaHostRegister 0.15 s (2 MB pages: 512x fewer to pin) = 28 GB/s; both copy D2H at the same 48 GB/s.
 #include "host_pool.hpp"
 
+#include <sched.h>
 #include <sys/mman.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -80,22 +82,94 @@ unsigned usable_cpus() {
     return hw;
 }
 
-void first_touch(char *p, size_t n, bool single) {
+// ---- NUMA placement -------------------------------------------------------------------------------------------------
+// The result blocks are the target of tens of GB of D2H traffic; on a two-socket box a block that lands on the socket the
+// GPU is NOT attached to is written across the inter-socket link (8 ranks downloading 19.2 GB at cfg 4: half of them took
+// 0.21 s instead of 0.13 s, profiles/r2_configs.md).  So the block is placed on the memory node of the current CUDA device:
+// mbind(MPOL_PREFERRED) where the container allows it, and the first-touch threads run on that node's CPUs either way
+// (first touch allocates locally).  Every step is best effort: unknown topology or a refused call leaves the old behaviour.
+// SVDLAS2_HOST_NUMA=0 switches it off.
+struct NodeInfo {
+    int node = -1;
+    cpu_set_t cpus;     // CPUs of the node that this process may run on
+    bool have_cpus = false;
+};
+
+bool read_line(const std::string &path, char *buf, size_t n) {
+    FILE *f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    const bool ok = std::fgets(buf, (int)n, f) != nullptr;
+    std::fclose(f);
+    return ok;
+}
+
+NodeInfo current_device_node() {
+    NodeInfo ni;
+    CPU_ZERO(&ni.cpus);
+    if (const char *e = std::getenv("SVDLAS2_HOST_NUMA")) if (e[0] == '0') return ni;
+    int dev = 0;
+    char bus[64] = {0};
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, (int)sizeof bus - 1, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return ni;
+    }
+    for (char *c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    char line[4096];
+    if (!read_line(std::string("/sys/bus/pci/devices/") + bus + "/numa_node", line, sizeof line)) return ni;
+    ni.node = std::atoi(line);
+    if (ni.node < 0) return ni;
+    // "0-31,64-95" -> set, intersected with what the process is allowed to use
+    if (!read_line("/sys/devices/system/node/node" + std::to_string(ni.node) + "/cpulist", line, sizeof line)) return ni;
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return ni;
+    int found = 0;
+    for (char *q = line; *q;) {
+        char *end = nullptr;
+        long a = std::strtol(q, &end, 10);
+        if (end == q) break;
+        long b = a;
+        if (*end == '-') { q = end + 1; b = std::strtol(q, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (c >= 0 && CPU_ISSET((int)c, &allowed)) { CPU_SET((int)c, &ni.cpus); found++; }
+        q = (*end == ',') ? end + 1 : end;
+        if (*end != ',' ) break;
+    }
+    ni.have_cpus = found > 0;
+    return ni;
+}
+
+// returns 0 when the kernel accepted the policy
+long prefer_node(void *p, size_t cap, int node) {
+    if (node < 0 || node >= 1024) return -1;
+    unsigned long mask[1024 / (8 * sizeof(unsigned long))] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+#ifdef SYS_mbind
+    return syscall(SYS_mbind, p, cap, 1 /* MPOL_PREFERRED */, mask, 1024ul + 1, 0u);
+#else
+    (void)p; (void)cap;
+    return -1;
+#endif
+}
+
+void first_touch(char *p, size_t n, bool single, const NodeInfo &ni) {
     static const unsigned want = [] {
         if (const char *e = std::getenv("SVDLAS2_TOUCH_THREADS")) return (unsigned)std::max(1, std::atoi(e));
         return std::max(1u, std::min(8u, usable_cpus() / 2)); // leave cores to the launching thread and the driver
     }();
     unsigned nt = want;
     if (n < (size_t)256 << 20 || single) nt = 1;
-    auto work = [p, n, nt](unsigned t) {
+    auto work = [p, n, nt, &ni](unsigned t, bool own_thread) {
+        // a helper thread moves to the device's memory node before it touches (the caller's affinity is left alone)
+        if (own_thread && ni.have_cpus) sched_setaffinity(0, sizeof ni.cpus, &ni.cpus);
         size_t a = n / nt * t, b = (t == nt - 1) ? n : n / nt * (t + 1);
         a = a / 4096 * 4096;
         for (size_t i = a; i < b; i += 4096) p[i] = 0;
     };
-    if (nt == 1) { work(0); return; }
+    if (nt == 1 && !ni.have_cpus) { work(0, false); return; }
     std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
-    work(0);
+    for (unsigned t = ni.have_cpus ? 0 : 1; t < nt; t++) th.emplace_back(work, t, true);
+    if (!ni.have_cpus) work(0, false);
     for (auto &x : th) x.join();
 }
 
@@ -107,6 +181,8 @@ void unmap_block(void *p, const Block &b) {
 } // namespace
 
 size_t host_prefetch_limit() { return phys_bytes() / 4; }
+
+int host_pool_node() { return current_device_node().node; }
 
 void *host_acquire(size_t bytes) {
     if (bytes == 0) bytes = 8;
@@ -132,7 +208,9 @@ void *host_acquire(size_t bytes) {
     if (mode != "nothp") madvise(p, cap, MADV_HUGEPAGE); // advisory: without THP the block is still correct, only slower to pin
     const bool trace = std::getenv("SVDLAS2_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    first_touch((char *)p, cap, mode == "touch1");
+    const NodeInfo ni = current_device_node();
+    const long bound = ni.node >= 0 ? prefer_node(p, cap, ni.node) : -1;
+    first_touch((char *)p, cap, mode == "touch1", ni);
     const auto t1 = std::chrono::steady_clock::now();
     Kind kind = Kind::Registered;
     if (cudaHostRegister(p, cap, cudaHostRegisterPortable) != cudaSuccess) {
@@ -140,10 +218,12 @@ void *host_acquire(size_t bytes) {
         kind = Kind::Pageable; // D2H still works (staged by the driver), just slower
     }
     if (trace)
-        fprintf(stderr, "[svdlas2] host pool: new block of %.3f GB: first touch %.3f s, cudaHostRegister %.3f s (%s)\n",
+        fprintf(stderr, "[svdlas2] host pool: new block of %.3f GB: first touch %.3f s, cudaHostRegister %.3f s (%s); memory node of the "
+                        "device %d (mbind %s, touch threads %s)\n",
                 (double)cap / 1e9, std::chrono::duration<double>(t1 - t0).count(),
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(),
-                kind == Kind::Registered ? "registered" : "pageable");
+                kind == Kind::Registered ? "registered" : "pageable", ni.node, ni.node < 0 ? "skipped" : bound == 0 ? "ok" : "refused",
+                ni.have_cpus ? "on that node" : "unbound");
     std::lock_guard<std::mutex> lk(P.mu);
     P.live[p] = Block{cap, kind};
     return p;

@@ -16,6 +16,8 @@ void *host_acquire(size_t bytes);
 void host_release(void *p);
 // Largest result (bytes) worth allocating ahead of time on a helper thread: 1/4 of the machine's RAM.
 size_t host_prefetch_limit();
+// Memory node the pool steers new blocks to: the node of the current CUDA device (-1: unknown / switched off).
+int host_pool_node();
 // Frees every cached buffer (tests; process exit does it implicitly).
 void host_pool_trim();
 

@@ -4,6 +4,8 @@
 #include <vector>
 
 #include "host_math.hpp"
+#include "host_pool.hpp"
+#include "util.cuh"
 
 using namespace las2;
 
@@ -54,6 +56,22 @@ int svdlas2_test_refine_bounds(int *enough, double endl, double endr, double *ri
     *enough = en ? 1 : 0;
     if (neig) *neig = ne;
     return rc;
+}
+
+int svdlas2_test_host_block(uint64_t bytes, int *node) {
+    try {
+        if (node) *node = host_pool_node();
+        char *p = static_cast<char *>(host_acquire(bytes));
+        p[0] = 1;
+        if (bytes) p[bytes - 1] = 1;
+        host_release(p);
+        host_pool_trim();
+        return 0;
+    } catch (const Error &e) {
+        return e.code;
+    } catch (...) {
+        return SVDLAS2_ERR_ALLOC;
+    }
 }
 
 void svdlas2_test_cosort(uint64_t n, double *keys, double *vals) { cosort_ascending(n, keys, vals); }

@@ -26,6 +26,8 @@ def hooks(las2):
     L.svdlas2_test_refine_bounds.restype = C.c_int
     L.svdlas2_test_cosort.argtypes = [C.c_uint64, f64p, f64p]
     L.svdlas2_test_cosort.restype = None
+    L.svdlas2_test_host_block.argtypes = [C.c_uint64, C.POINTER(C.c_int)]
+    L.svdlas2_test_host_block.restype = C.c_int
     return L
 
 
@@ -143,3 +145,12 @@ def test_cosort(hooks):
     hooks.svdlas2_test_cosort(50, p(k1), p(v1))
     order = np.argsort(k, kind="stable")
     assert np.array_equal(k1, k[order]) and np.array_equal(v1, v[order])
+
+
+@pytest.mark.parametrize("nbytes", [1, 3 << 20, 300 << 20])
+def test_host_result_block_without_a_device(hooks, nbytes):
+    """The pool of host result buffers (host_pool.cpp) hands out a usable block whether or not a device / its memory
+    node can be found: placement on the device's NUMA node is best effort, never a failure."""
+    node = C.c_int(-7)
+    assert hooks.svdlas2_test_host_block(nbytes, C.byref(node)) == 0
+    assert node.value >= -1
