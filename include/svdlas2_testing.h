@@ -48,6 +48,13 @@ SVDLAS2_API int svdlas2_test_spmm4(svdlas2_operator *op, uint32_t nv, const doub
  * DMMA result from a host-computed double-double reference on a sample of entries, same scale. */
 SVDLAS2_API int svdlas2_test_time_ritz(uint64_t n, uint32_t js, uint32_t d, int reps, int device, double ms[2], double *max_diff,
                                        double *max_err);
+/* GPU test / tuning hook for the device half of imtql2 (src/lib.rs:1646-1652): runs the host recurrences on (d, e) (both
+ * overwritten, d = ascending eigenvalues), replays the recorded rotations on the GPU `reps` times and returns z (n x n row-major,
+ * logical column order) exactly as svdlas2_test_ql_vectors does on the CPU -- the two must agree BIT FOR BIT.  variant: 0 = one
+ * replaying warp per CTA, 1 = the sweeps pipelined over the warps of the CTA, -1 = the library's default.  ms = wall time of one
+ * replay incl. the upload of the plan (reps >= 2). */
+SVDLAS2_API int svdlas2_test_ql_replay(uint64_t n, double *d, double *e, double *z, int variant, int reps, int device, double *ms,
+                                       uint64_t *n_rotations);
 /* How the upload laid the operator out: out[0] = 1 when the N side was relabelled by popularity, out[1] = share of B's column
  * indices inside the shared-memory prefix (hot_fraction), out[2] = size of that prefix, out[3] / out[4] = mode of B's / B''s
  * first stream and out[5] of B''s second one (-1 none, 0 plain, 1 plain + hot prefix, 2 slab-local, 3 wide slabs),

@@ -1,5 +1,6 @@
 // abi.cu -- the extern "C" boundary declared in include/svdlas2.h.  Exceptions never cross it: every entry
 // point maps las2::Error (and anything else) to a status code and a thread-local message.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -9,6 +10,7 @@
 #include "las2.hpp"
 #include "../../include/svdlas2_testing.h"
 #include "spmv.cuh"
+#include "tridiag_device.cuh"
 
 using namespace las2;
 
@@ -386,6 +388,35 @@ int svdlas2_test_time_ritz(uint64_t n, uint32_t js, uint32_t d, int reps, int de
             }
         if (max_diff) *max_diff = vmax > 0 ? dmax / vmax : dmax;
         if (max_err) *max_err = vmax > 0 ? emax / vmax : emax;
+    });
+}
+
+int svdlas2_test_ql_replay(uint64_t n, double *d, double *e, double *z, int variant, int reps, int device, double *ms,
+                           uint64_t *n_rotations) {
+    if (n == 0 || !d || !e || !z || reps < 1) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        if (device >= 0) LAS2_CUDA(cudaSetDevice(device));
+        QlPlan plan;
+        const int rc = ql_rotations(n, d, e, plan);
+        if (rc) throw Error(rc, "imtql2 did not converge");
+        if (n_rotations) *n_rotations = plan.rotations();
+        cudaStream_t s;
+        LAS2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        struct SDel { cudaStream_t s; ~SDel() { cudaStreamDestroy(s); } } sdel{s};
+        const u32 js = (u32)n, ldz = (u32)((n + 31) / 32 * 32);
+        DevBuf<double> zT((size_t)ldz * js);
+        struct VReset { ~VReset() { g_ql_replay_variant = -1; } } vreset;
+        g_ql_replay_variant = variant;
+        LAS2_CUDA(cudaMemsetAsync(zT.get(), 0xff, (size_t)ldz * js * sizeof(double), s)); // NaN: every entry must be written
+        ql_replay(plan, js, ldz, zT.get(), s, nullptr, nullptr); // (synchronises the stream itself)
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 1; r < reps; r++) ql_replay(plan, js, ldz, zT.get(), s, nullptr, nullptr);
+        LAS2_CUDA(cudaStreamSynchronize(s));
+        if (ms) *ms = reps > 1 ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (reps - 1) : 0.0;
+        std::vector<double> h((size_t)ldz * js);
+        LAS2_CUDA(cudaMemcpy(h.data(), zT.get(), h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (u64 row = 0; row < n; row++)
+            for (u64 k = 0; k < n; k++) z[row * n + k] = h[(size_t)plan.column_of[k] * ldz + row];
     });
 }
 

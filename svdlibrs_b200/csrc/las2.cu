@@ -68,6 +68,9 @@ struct Solver {
     unsigned long long chain_seq = 0;
     u64 spec_col = ~(u64)0;
     bool use_chain = false;
+    // small operators (plain CSR, short rows, one GPU): the two SpMVs of svd_opb run inside the chain's launch as well
+    bool use_fused = false;
+    StepSpmv fused{};
     // host (WorkSpace arrays, src/lib.rs:770-775)
     std::vector<double> alf, bet, eta, oldeta, ritz, bnd, w5;
     svdlas2_profile prof;
@@ -100,6 +103,23 @@ struct Solver {
             if (use_chain) {
                 chain_work.alloc(6 * (size_t)kMaxParts + 1);
                 LAS2_CUDA(cudaMemsetAsync(chain_work.get(), 0, (6 * (size_t)kMaxParts + 1) * sizeof(double), s));
+            }
+            const char *f = std::getenv("SVDLAS2_STEP_FUSED");
+            if (use_chain && !(f && f[0] == '0') && !op.ring && !op.comm && !op.profile && !op.B.chk.active && !op.BT.chk.active &&
+                M > 0 && N > 0 && op.B.nnz > 0 && M < (1ull << 31) && N < (1ull << 31)) {
+                auto lanes_for = [&](const DeviceCsr &A, u64 rows, int *lanes) {
+                    const u32 longest = csr_max_row_len(A.off.get(), (u32)rows, s);
+                    int l = step_spmv_lanes((double)A.nnz / (double)rows);
+                    while (l < 32 && longest > step_spmv_max_row(l)) l <<= 1;
+                    *lanes = l;
+                    return longest <= step_spmv_max_row(l);
+                };
+                int lb = 0, lbt = 0;
+                if (lanes_for(op.B, M, &lb) && lanes_for(op.BT, N, &lbt)) {
+                    use_fused = true;
+                    fused = StepSpmv{op.B.off.get(), op.B.idx.get(), op.B.val.get(), (u32)M, lb,
+                                     op.BT.off.get(), op.BT.idx.get(), op.BT.val.get(), (u32)N, lbt, t.get()};
+                }
             }
         }
         alf.assign(iters, 0.0); eta.assign(iters, 0.0); oldeta.assign(iters, 0.0);
@@ -342,7 +362,9 @@ struct Solver {
             constexpr int s_alf = 7;
             const bool chain_now = use_chain && j > kMaxLL;
             const bool fold_epilogue = chain_now && !op.ring; // single GPU: the update r -= rnm q_{j-1} becomes the chain's first phase
-            if (fold_epilogue) opb(q(j), r.get());
+            const bool fused_now = fold_epilogue && use_fused; // svd_opb itself runs inside the chain's launch
+            if (fused_now) { prof.n_opb += 1; prof.n_spmv += 2; }
+            else if (fold_epilogue) opb(q(j), r.get());
             else opb_step(q(j), q(j - 1), rn, slot[s_alf]);
             if (j <= kMaxLL) {
                 // |alf[j-1]| > 4 |alf[j]| decides ll only while j <= MAXLL (:1282): needs alf[j] now
@@ -378,7 +400,8 @@ struct Solver {
                 c.coef0 = rn;
                 c.q_next = speculate ? q(j + 1) : nullptr;
                 chain_seq += 1;
-                vec_step_chain(r.get(), ld, c, chain_work.get(), hs.get(), chain_seq, s);
+                if (fused_now) vec_step_fused(r.get(), ld, c, fused, chain_work.get(), hs.get(), chain_seq, s);
+                else vec_step_chain(r.get(), ld, c, chain_work.get(), hs.get(), chain_seq, s);
                 prof.n_kernel_launches += 1;
                 wait_chain(v);
                 if (speculate) spec_col = j + 1;

@@ -8,6 +8,7 @@ namespace las2 {
 
 // zT (device): js columns x ldz rows, zT[col * ldz + row] = z[row][col] of the reference's row-major z.
 // Sets zT = I, uploads the plan and replays every rotation; one thread per row of z (rows are independent).
+extern int g_ql_replay_variant; // test hook: -1 default, 0 one replaying warp per CTA, 1 pipeline of sweeps over 8 warps
 void ql_replay(const QlPlan &plan, u32 js, u32 ldz, double *zT, cudaStream_t s, u64 *launches, u64 *h2d_bytes);
 
 // C[i * d + c] = z[(js-1-i)][logical column k_c] = zT[phys_cols[c] * ldz + (js-1-i)]   (T was reversed, :1790-1791)

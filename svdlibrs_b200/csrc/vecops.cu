@@ -153,8 +153,46 @@ __device__ __forceinline__ void chain_barrier(unsigned *count, unsigned *gen) {
     __syncthreads();
 }
 
+// y_row = sum_k val[k] * x[idx[k]] for the rows of a CSR matrix, one sub-warp of L lanes per row; emit(row, value) runs on the
+// sub-warp's first lane.  COHERENT: x was written earlier in this launch by other CTAs (read it through L2, not the
+// non-coherent path).  All 32 lanes of a warp make the same number of trips (the shuffles need them all).
+template <int L, bool COHERENT, class Emit>
+__device__ __forceinline__ void subwarp_spmv(const u32 *__restrict__ off, const u32 *__restrict__ idx,
+                                             const double *__restrict__ val, u32 rows, const double *x, Emit emit) {
+    const u32 lane = threadIdx.x & (L - 1);
+    const u32 sub = ((u32)blockIdx.x * blockDim.x + threadIdx.x) / L;
+    const u32 nsub = (u32)gridDim.x * blockDim.x / L;
+    const u32 sub_in_warp = (threadIdx.x & 31u) / L;
+    for (u32 base = sub - sub_in_warp; base < rows; base += nsub) {
+        const u32 row = base + sub_in_warp;
+        u32 b = 0, e = 0;
+        if (row < rows) { b = off[row]; e = off[row + 1]; }
+        double acc = 0.0;
+        for (u32 k = b + lane; k < e; k += L) {
+            const double xv = COHERENT ? __ldcg(x + idx[k]) : __ldg(x + idx[k]);
+            acc = fma(val[k], xv, acc);
+        }
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && row < rows) emit(row, acc);
+    }
+}
+
+template <bool COHERENT, class Emit>
+__device__ __forceinline__ void subwarp_spmv_any(int lanes, const u32 *off, const u32 *idx, const double *val, u32 rows,
+                                                 const double *x, Emit emit) {
+    switch (lanes) {
+    case 2: subwarp_spmv<2, COHERENT>(off, idx, val, rows, x, emit); break;
+    case 4: subwarp_spmv<4, COHERENT>(off, idx, val, rows, x, emit); break;
+    case 8: subwarp_spmv<8, COHERENT>(off, idx, val, rows, x, emit); break;
+    case 16: subwarp_spmv<16, COHERENT>(off, idx, val, rows, x, emit); break;
+    default: subwarp_spmv<32, COHERENT>(off, idx, val, rows, x, emit); break;
+    }
+}
+
+template <bool SPMV>
 __global__ void __launch_bounds__(1024)
-k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, double *__restrict__ work, double *__restrict__ host_out,
+k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, StepSpmv m, double *__restrict__ work, double *__restrict__ host_out,
              unsigned long long seq) {
     unsigned *bar = reinterpret_cast<unsigned *>(work + 6 * (size_t)kMaxParts);
     __shared__ double sm[32];
@@ -162,7 +200,32 @@ k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, double *__restrict__ 
     double coef_seen[6];
     const double *parts = c.alf_parts;
     int nparts = c.alf_nparts;
-    for (int k = 0; k < c.nphases; k++) {
+    int k0 = 0;
+    if (SPMV) {
+        // ---- svd_opb and the step's first update in place of the chain's phase 0 ----
+        const double *x = c.y[0];     // q_j
+        const double *qprev = c.x[0]; // q_{j-1}
+        double *t = m.t;
+        subwarp_spmv_any<false>(m.b_lanes, m.b_off, m.b_idx, m.b_val, m.b_rows, x, [t](u32 row, double v) { t[row] = v; });
+        chain_barrier(bar, bar + 1);
+        const double nc = -c.coef0;
+        double *rs = reinterpret_cast<double *>(r);
+        double acc = 0.0;
+        subwarp_spmv_any<true>(m.bt_lanes, m.bt_off, m.bt_idx, m.bt_val, m.bt_rows, t, [&](u32 row, double v) {
+            const double rv = __dadd_rn(v, __dmul_rn(nc, qprev[row])); // svd_daxpy(-rnm, q_{j-1}, r), :1277
+            rs[row] = rv;
+            acc = fma(rv, x[row], acc);                                // alf = r . q_j, :1278
+        });
+        __syncthreads();
+        const double tsum = cta_reduce(acc, sm);
+        if (threadIdx.x == 0) work[blockIdx.x] = tsum;
+        parts = work;
+        nparts = (int)gridDim.x;
+        coef_seen[0] = c.coef0;
+        chain_barrier(bar, bar + 1);
+        k0 = 1;
+    }
+    for (int k = k0; k < c.nphases; k++) {
         const double coef = (k == 0 && parts == nullptr) ? c.coef0 : cta_sum_partials(parts, nparts, &cs);
         coef_seen[k] = coef;
         const double nc = -coef;
@@ -209,6 +272,14 @@ k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, double *__restrict__ 
     }
 }
 
+__global__ void __launch_bounds__(256) k_max_row_len(const u32 *__restrict__ off, u32 rows, u32 *__restrict__ out) {
+    u32 best = 0;
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) best = max(best, off[r + 1] - off[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(out, best);
+}
+
 // out[i * n + c] = V[i * ld + old2new[c]]: the N-side singular vectors back in the caller's numbering (coalesced writes)
 __global__ void __launch_bounds__(kVecThreads)
 k_unpermute_rows(const double *__restrict__ V, u64 ld, u64 n, const u32 *__restrict__ old2new, double *__restrict__ out) {
@@ -252,7 +323,39 @@ void vec_step_chain(double *r, u64 ld, const StepChain &c, double *work, double 
     if (grid == 0) throw Error(SVDLAS2_ERR_CUDA, "step chain: no device");
     // one CTA per SM at most (the in-kernel barrier): long vectors get 1024 threads per CTA to keep enough loads in flight
     const unsigned threads = n2 > (u64)grid * kVecThreads * 2 ? 1024u : (unsigned)kVecThreads;
-    k_step_chain<<<grid, threads, 0, s>>>(reinterpret_cast<double2 *>(r), n2, c, work, host_out, seq);
+    k_step_chain<false><<<grid, threads, 0, s>>>(reinterpret_cast<double2 *>(r), n2, c, StepSpmv{}, work, host_out, seq);
+    LAS2_LAUNCH_CHECK();
+}
+
+int step_spmv_lanes(double mean_row_len) {
+    int lanes = 2;
+    while (lanes < 32 && (double)lanes < mean_row_len * 0.5) lanes <<= 1;
+    return lanes;
+}
+
+u32 csr_max_row_len(const u32 *off, u32 rows, cudaStream_t s) {
+    if (rows == 0) return 0;
+    DevBuf<u32> out(1);
+    LAS2_CUDA(cudaMemsetAsync(out.get(), 0, sizeof(u32), s));
+    const unsigned grid = (unsigned)std::min<u64>(((u64)rows + 255) / 256, (u64)kNumSMs * 8);
+    k_max_row_len<<<grid, 256, 0, s>>>(off, rows, out.get());
+    LAS2_LAUNCH_CHECK();
+    u32 h = 0;
+    LAS2_CUDA(cudaMemcpyAsync(&h, out.get(), sizeof(u32), cudaMemcpyDeviceToHost, s));
+    LAS2_CUDA(cudaStreamSynchronize(s));
+    return h;
+}
+
+void vec_step_fused(double *r, u64 ld, const StepChain &c, const StepSpmv &m, double *work, double *host_out, unsigned long long seq,
+                    cudaStream_t s) {
+    const u64 n2 = ld / 2;
+    const unsigned max_grid = step_chain_max_grid();
+    if (max_grid == 0) throw Error(SVDLAS2_ERR_CUDA, "fused step: no device");
+    // enough threads that every row of the larger product gets its sub-warp in about one pass (one CTA per SM at most)
+    const u64 want = std::max<u64>({(u64)m.b_rows * (u64)m.b_lanes, (u64)m.bt_rows * (u64)m.bt_lanes, n2});
+    const unsigned threads = want > (u64)max_grid * 256 ? 1024u : 256u;
+    const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>(max_grid, (want + threads - 1) / threads));
+    k_step_chain<true><<<grid, threads, 0, s>>>(reinterpret_cast<double2 *>(r), n2, c, m, work, host_out, seq);
     LAS2_LAUNCH_CHECK();
 }
 

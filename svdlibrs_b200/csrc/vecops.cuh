@@ -63,6 +63,24 @@ struct StepChain {
     double coef0;
     double *q_next;           // may be nullptr
 };
+// The whole Lanczos step of a SMALL operator in the same launch (single GPU, both matrices in plain CSR, short rows): two more
+// leading phases compute t = B x and r = B' t - coef0 * qprev with the partials of r . x (svd_opb, src/lib.rs:829-837, plus
+// :1276-1278), so that a step is ONE launch and one polled flag instead of 5-6 launches.  Rows are handed to sub-warps of
+// `lanes` threads (2..32, chosen from the mean row length); a lane adds its strided elements in order (fma), a fixed xor
+// tree joins the lanes: deterministic, independent of the grid.  The chain then starts at phase 1 (phase 0 of `StepChain` must
+// be the folded epilogue: x[0] = qprev, y[0] = x, alf_parts = nullptr).
+struct StepSpmv {
+    const u32 *b_off, *b_idx;   const double *b_val;   u32 b_rows;  int b_lanes;   // B  (M x N)
+    const u32 *bt_off, *bt_idx; const double *bt_val;  u32 bt_rows; int bt_lanes;  // B' (N x M)
+    double *t;                  // M doubles of scratch
+};
+// sub-warp width for rows of the given mean length / the longest row such a launch still takes
+int step_spmv_lanes(double mean_row_len);
+inline u32 step_spmv_max_row(int lanes) { return 64u * (u32)lanes; }
+// longest row of a CSR matrix (one small kernel + one synchronising read-back)
+u32 csr_max_row_len(const u32 *off, u32 rows, cudaStream_t s);
+void vec_step_fused(double *r, u64 ld, const StepChain &c, const StepSpmv &m, double *work, double *host_out, unsigned long long seq,
+                    cudaStream_t s);
 // work: 6 * kMaxParts doubles of partial scratch + 2 unsigned ints (ZEROED once by the caller: the launch's grid barrier);
 // host_out: 4 doubles + 1 sequence word (pinned).  The grid is at most one CTA per SM.
 void vec_step_chain(double *r, u64 ld, const StepChain &c, double *work, double *host_out, unsigned long long seq, cudaStream_t s);

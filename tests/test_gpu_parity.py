@@ -579,22 +579,73 @@ def test_ritz_contraction_variants_agree(las2, n, js, d):
 
 
 def test_step_chain_matches_oracle_and_the_kernel_chain(las2, oracle, monkeypatch):
-    """The local re-orthogonalisation of a Lanczos step (reference src/lib.rs:1279-1304) as ONE cooperative launch with the
-    scalars polled from pinned memory and the next Lanczos vector written speculatively (vec_step_chain), against the oracle
-    and against the chain of separate kernels: identical counts, sigma to 1e-10, vectors to 1 - 1e-8; covers ll = 0 and
+    """The local re-orthogonalisation of a Lanczos step (reference src/lib.rs:1279-1304) as ONE launch with an in-kernel grid
+    barrier, the scalars polled from pinned memory and the next Lanczos vector written speculatively (vec_step_chain), and the
+    whole step incl. svd_opb (:829-837) in that launch for small operators (vec_step_fused), against the oracle and against
+    the chain of separate kernels: identical counts, sigma to 1e-10, vectors to 1 - 1e-8; covers ll = 0 and
     ll > 0 (extra phases), purge steps (speculation discarded) and the restart path."""
     from svdlibrs_b200 import synthetic
     cases = [(synthetic.make("cfg1")[0], 20), (synthetic.make("cfg2", scale=0.02)[0], 30), (synthetic.make("cfg3", scale=0.01)[0], 15),
              (sp.random(400, 300, density=0.05, format="csr", random_state=3), 10),
              (sp.coo_matrix(([3.0, 4.0], ([1, 2], [0, 1])), shape=(4, 4)).tocsr(), 3), (sp.identity(3, format="csc"), 0)]
-    for A, dims in cases:
+    for case, (A, dims) in enumerate(cases):
         monkeypatch.setenv("SVDLAS2_STEP_CHAIN", "0")
         plain = las2.svd_dim_seed(A, dims, 12345)
-        monkeypatch.setenv("SVDLAS2_STEP_CHAIN", "1")
-        got = las2.svd_dim_seed(A, dims, 12345)
         ref = oracle.svd_dim_seed(A, dims, 12345)
-        assert_svd_parity(got, ref)
-        assert got.diagnostics == plain.diagnostics
-        assert np.allclose(got.s, plain.s, rtol=1e-12, atol=0)
+        monkeypatch.setenv("SVDLAS2_STEP_CHAIN", "1")
+        launches = {}
+        # the chain alone, then with svd_opb inside the same launch (k_step_chain<true>: small operators in plain CSR)
+        for fused in ("0", "1"):
+            monkeypatch.setenv("SVDLAS2_STEP_FUSED", fused)
+            got = las2.svd_dim_seed(A, dims, 12345)
+            assert_svd_parity(got, ref)
+            assert got.diagnostics == plain.diagnostics
+            assert np.allclose(got.s, plain.s, rtol=1e-12, atol=0)
+            launches[fused] = got.profile["n_kernel_launches"]
+            assert got.profile["n_opb"] == plain.profile["n_opb"]
         if min(A.shape) > 100:
-            assert got.profile["n_kernel_launches"] < plain.profile["n_kernel_launches"]
+            assert launches["1"] <= launches["0"] < plain.profile["n_kernel_launches"]
+        if case in (0, 3):  # uniform rows: short enough for the sub-warp SpMV, so svd_opb costs no launch of its own
+            assert launches["1"] < launches["0"]
+    # a row too long for the sub-warp SpMV (> 64 x 32 entries) keeps the separate SpMV kernels
+    rng = np.random.default_rng(5)
+    A = sp.random(3000, 2600, density=0.002, format="lil", random_state=8)
+    A[7, :] = rng.random(2600)
+    A = A.tocsr()
+    monkeypatch.setenv("SVDLAS2_STEP_FUSED", "1")
+    got = las2.svd_dim_seed(A, 8, 12345)
+    assert_svd_parity(got, oracle.svd_dim_seed(A, 8, 12345))
+    monkeypatch.setenv("SVDLAS2_STEP_FUSED", "0")
+    assert got.profile["n_kernel_launches"] == las2.svd_dim_seed(A, 8, 12345).profile["n_kernel_launches"]
+
+
+@pytest.mark.parametrize("n,seed,clustered", [(2, 0, False), (3, 1, False), (33, 2, False), (64, 4, True), (263, 5, False),
+                                               (801, 6, False), (1700, 7, False)])
+def test_ql_replay_on_the_gpu_is_bit_identical(las2, n, seed, clustered):
+    """The O(js^3) half of imtql2 (reference src/lib.rs:1646-1652) on the GPU: the rotation plan replayed by one warp per CTA
+    and by the pipeline of sweeps over the warps of a CTA (wavefront; js = 801 and 1700 also exercise fewer than 32 rows per
+    CTA) against the CPU replay of the same plan, which test_host_logic pins bit for bit on the oracle's imtql2."""
+    import ctypes as C
+    from svdlibrs_b200 import _lib
+    L = _lib.lib()
+    f64p = C.POINTER(C.c_double)
+    L.svdlas2_test_ql_vectors.argtypes = [C.c_uint64, f64p, f64p, f64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.svdlas2_test_ql_vectors.restype = C.c_int
+    L.svdlas2_test_ql_replay.argtypes = [C.c_uint64, f64p, f64p, f64p, C.c_int, C.c_int, C.c_int, f64p, C.POINTER(C.c_uint64)]
+    L.svdlas2_test_ql_replay.restype = C.c_int
+    rng = np.random.default_rng(seed)
+    d = rng.standard_normal(n) if not clustered else 1.0 + 1e-9 * rng.standard_normal(n)
+    e = np.concatenate(([0.0], np.abs(rng.standard_normal(n - 1)) * (1e-3 if clustered else 1.0)))
+    p = lambda a: a.ctypes.data_as(f64p)
+    d0, e0, z0 = d.copy(), e.copy(), np.zeros((n, n))
+    assert L.svdlas2_test_ql_vectors(n, p(d0), p(e0), p(z0), None, None) == 0
+    times = {}
+    for variant in (0, 1, -1):
+        d1, e1, z1 = d.copy(), e.copy(), np.full((n, n), np.nan)
+        ms, nrot = C.c_double(), C.c_uint64()
+        rc = L.svdlas2_test_ql_replay(n, p(d1), p(e1), p(z1), variant, 3, -1, C.byref(ms), C.byref(nrot))
+        assert rc == 0, L.svdlas2_last_error()
+        assert np.array_equal(d1, d0)
+        assert np.array_equal(z1, z0), f"variant {variant}: {np.count_nonzero(z1 != z0)} entries differ"
+        times[variant] = ms.value
+    print(f"[ql replay] n={n} rotations={nrot.value}: one warp {times[0]:.3f} ms, pipeline {times[1]:.3f} ms")
