@@ -225,6 +225,12 @@ k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, StepSpmv m, double *_
         chain_barrier(bar, bar + 1);
         k0 = 1;
     }
+    // Short vectors (SPMV launches only): ONE CTA runs the remaining phases, so that the 3-5 dependent reductions cost a block
+    // barrier each instead of a grid barrier (a few us each with 148 CTAs); the other CTAs are done.
+    const bool solo = SPMV && m.solo_tail;
+    if (solo && blockIdx.x != 0) return;
+    const u64 first = solo ? threadIdx.x : (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = solo ? blockDim.x : (u64)gridDim.x * blockDim.x;
     for (int k = k0; k < c.nphases; k++) {
         const double coef = (k == 0 && parts == nullptr) ? c.coef0 : cta_sum_partials(parts, nparts, &cs);
         coef_seen[k] = coef;
@@ -232,8 +238,9 @@ k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, StepSpmv m, double *_
         const double2 *__restrict__ x = reinterpret_cast<const double2 *>(c.x[k]);
         const double2 *__restrict__ y = reinterpret_cast<const double2 *>(c.y[k]);
         double acc = 0.0;
-        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (u64)gridDim.x * blockDim.x) {
-            double2 rv = r[i];
+        for (u64 i = first; i < n2; i += stride) {
+            // (right after the SpMV phase r holds what OTHER CTAs stored in this launch: read it through L2)
+            double2 rv = (SPMV && k == k0) ? __ldcg(r + i) : r[i];
             const double2 xv = x[i];
             rv.x = __dadd_rn(rv.x, __dmul_rn(nc, xv.x)); // svd_daxpy(-c, x, r)
             rv.y = __dadd_rn(rv.y, __dmul_rn(nc, xv.y));
@@ -245,17 +252,18 @@ k_step_chain(double2 *__restrict__ r, u64 n2, StepChain c, StepSpmv m, double *_
         __syncthreads(); // sm / cs are reused by the next phase
         const double t = cta_reduce(acc, sm);
         double *out = work + (size_t)k * kMaxParts;
-        if (threadIdx.x == 0) out[blockIdx.x] = t;
+        if (threadIdx.x == 0) out[solo ? 0 : blockIdx.x] = t;
         parts = out;
-        nparts = (int)gridDim.x;
-        chain_barrier(bar, bar + 1);
+        nparts = solo ? 1 : (int)gridDim.x;
+        if (solo) __syncthreads();
+        else chain_barrier(bar, bar + 1);
     }
     const double nrm2 = cta_sum_partials(parts, nparts, &cs);
     if (c.q_next) {
         // q_{j+1} = r / rnm exactly as the host-launched k_scale would form it (rnm = sqrt(|r|^2), alpha = 1 / rnm)
         const double alpha = 1.0 / sqrt(nrm2);
         double2 *__restrict__ qn = reinterpret_cast<double2 *>(c.q_next);
-        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (u64)gridDim.x * blockDim.x) {
+        for (u64 i = first; i < n2; i += stride) {
             double2 v = r[i];
             v.x = __dmul_rn(alpha, v.x);
             v.y = __dmul_rn(alpha, v.y);
@@ -355,7 +363,9 @@ void vec_step_fused(double *r, u64 ld, const StepChain &c, const StepSpmv &m, do
     const u64 want = std::max<u64>({(u64)m.b_rows * (u64)m.b_lanes, (u64)m.bt_rows * (u64)m.bt_lanes, n2});
     const unsigned threads = want > (u64)max_grid * 256 ? 1024u : 256u;
     const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>(max_grid, (want + threads - 1) / threads));
-    k_step_chain<true><<<grid, threads, 0, s>>>(reinterpret_cast<double2 *>(r), n2, c, m, work, host_out, seq);
+    StepSpmv mm = m;
+    mm.solo_tail = n2 <= 16384 ? 1 : 0; // <= 16 double2 per thread of one 1024-thread CTA
+    k_step_chain<true><<<grid, mm.solo_tail ? 1024u : threads, 0, s>>>(reinterpret_cast<double2 *>(r), n2, c, mm, work, host_out, seq);
     LAS2_LAUNCH_CHECK();
 }
 

@@ -73,6 +73,7 @@ struct StepSpmv {
     const u32 *b_off, *b_idx;   const double *b_val;   u32 b_rows;  int b_lanes;   // B  (M x N)
     const u32 *bt_off, *bt_idx; const double *bt_val;  u32 bt_rows; int bt_lanes;  // B' (N x M)
     double *t;                  // M doubles of scratch
+    int solo_tail;              // set by vec_step_fused: the vector phases run on one CTA (short vectors)
 };
 // sub-warp width for rows of the given mean length / the longest row such a launch still takes
 int step_spmv_lanes(double mean_row_len);
