@@ -18,7 +18,11 @@
 #include "las2.hpp"
 
 #include <chrono>
+#include <atomic>
+#include <condition_variable>
 #include <future>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -118,7 +122,7 @@ struct Solver {
                 if (lanes_for(op.B, M, &lb) && lanes_for(op.BT, N, &lbt)) {
                     use_fused = true;
                     fused = StepSpmv{op.B.off.get(), op.B.idx.get(), op.B.val.get(), (u32)M, lb,
-                                     op.BT.off.get(), op.BT.idx.get(), op.BT.val.get(), (u32)N, lbt, t.get()};
+                                     op.BT.off.get(), op.BT.idx.get(), op.BT.val.get(), (u32)N, lbt, t.get(), 0};
                 }
             }
         }
@@ -378,7 +382,7 @@ struct Solver {
                 // ---- :1277-1304 as ONE launch (vec_step_chain), scalars through pinned memory ----
                 const u64 lim = std::min<u64>(j - 1, *ll);
                 static const bool spec_on = [] { const char *e = std::getenv("SVDLAS2_CHAIN_SPEC"); return !(e && e[0] == '0'); }();
-                const bool speculate = spec_on && j + 1 < last;
+                const bool speculate = spec_on && (j + 1 < last || j + 1 < spec_horizon);
                 if (speculate) ensure_cols(j + 2);
                 StepChain c;
                 const int o = fold_epilogue ? 1 : 0; // phases shift by one when the epilogue leads the chain
@@ -448,13 +452,67 @@ struct Solver {
         return j;
     }
 
+    // ---- the analysis of T at the end of a batch (src/lib.rs:1975-2010): eigenvalues + last-row eigenvector components of
+    // every unreduced block, error bounds, number of stabilised Ritz values.  Reads alf[0..j] and betv[0..j+1]; writes ritz /
+    // bnd / w5 only, so it may run next to the Lanczos steps (lanso_overlapped). ----
+    void analyze_T(u64 j, double rnm, double tol, const double *betv, bool *enough, u64 *neig) {
+        const double ta0 = wall();
+        struct TAcc { double &acc; double t0; ~TAcc() { acc += wall() - t0; } } tacc{t_analysis_host, ta0};
+        u64 l = 0;
+        for (u64 id2 = 0; id2 < j; id2++) {
+            if (l > j) break;
+            u64 i = l;
+            while (i <= j && !near(betv[i + 1], 0.0)) i++;
+            i = std::min(i, j);
+            const u64 sz = i - l;
+            for (u64 k = 0; k <= sz; k++) ritz[l + sz - k] = alf[l + k];     // svd_dcopy reverses, :1985
+            for (u64 k = 0; k < sz; k++) w5[l + 1 + (sz - 1) - k] = betv[l + 1 + k]; // :1986
+            int rc = ql_values(sz + 1, &ritz[l], &w5[l], &bnd[l]);
+            if (rc == SVDLAS2_ERR_IMTQLB)
+                throw Error(rc, "imtqlb no convergence to an eigenvalue after 30 iterations");
+            if (rc) throw Error(rc, "imtqlb: expected 'm' to be non-zero");
+            for (u64 m = l; m <= i; m++) bnd[m] = rnm * std::fabs(bnd[m]);
+            l = i + 1;
+        }
+        cosort_ascending(j + 1, ritz.data(), bnd.data());
+        size_t ne = 0;
+        int rc = refine_bounds(enough, endl_, endr_, ritz.data(), bnd.data(), j, tol, &ne);
+        if (rc) throw Error(rc, "error_bound: expected 'step' to be non-zero");
+        *neig = ne;
+    }
+    double endl_ = 0.0, endr_ = 0.0;
+
+    // the batch scheduler (:1996-2009): returns the next `last`, or sets *enough
+    u64 next_last(u64 first, u64 j, u64 neig, u64 *intro, bool *enough) const {
+        u64 last = first;
+        if (neig < dims) {
+            if (neig == 0) {
+                last = first + 9;
+                *intro = first;
+            } else {
+                last = first + std::max<u64>(3, 1 + ((j - *intro) * (dims - neig)) / neig);
+            }
+            last = std::min(last, iters);
+        } else {
+            *enough = true;
+        }
+        *enough = *enough || first >= iters;
+        return last;
+    }
+
     // ---- lanso (src/lib.rs:1925-2017) ----
     u64 lanso(const double end_interval[2], uint32_t seed, u64 *neig_out) {
-        const double endl = end_interval[0], endr = end_interval[1];
+        endl_ = end_interval[0];
+        endr_ = end_interval[1];
         double rnm, tol;
         stpone(seed, &rnm, &tol);
         eta[0] = eps1;
         oldeta[0] = eps1;
+        // One GPU: the Lanczos recurrence does not depend on the analyses (they only decide where it STOPS), so the analyses
+        // run on a helper thread while the steps go on.  Sharded runs keep the sequential schedule: every rank must launch the
+        // same collectives, and how far a rank runs ahead of its helper depends on timing.
+        const char *e = std::getenv("SVDLAS2_OVERLAP_ANALYSIS");
+        if (!op.comm && !(e && e[0] == '0')) return lanso_overlapped(rnm, tol, neig_out);
         u64 ll = 0, first = 1;
         u64 last = std::min(iters, std::max<u64>(dims, 8) + dims);
         bool enough = false;
@@ -466,49 +524,168 @@ struct Solver {
             j = enough ? steps - 1 : last - 1;
             first = j + 1;
             bet[first] = rnm;
-
-            // analyze T: eigenvalues + last-row eigenvector components of every unreduced block
-            const double ta0 = wall();
-            struct TAcc { double &acc; double t0; ~TAcc() { acc += wall() - t0; } } tacc{t_analysis_host, ta0};
-            u64 l = 0;
-            for (u64 id2 = 0; id2 < j; id2++) {
-                if (l > j) break;
-                u64 i = l;
-                while (i <= j && !near(bet[i + 1], 0.0)) i++;
-                i = std::min(i, j);
-                const u64 sz = i - l;
-                for (u64 k = 0; k <= sz; k++) ritz[l + sz - k] = alf[l + k];     // svd_dcopy reverses, :1985
-                for (u64 k = 0; k < sz; k++) w5[l + 1 + (sz - 1) - k] = bet[l + 1 + k]; // :1986
-                int rc = ql_values(sz + 1, &ritz[l], &w5[l], &bnd[l]);
-                if (rc == SVDLAS2_ERR_IMTQLB)
-                    throw Error(rc, "imtqlb no convergence to an eigenvalue after 30 iterations");
-                if (rc) throw Error(rc, "imtqlb: expected 'm' to be non-zero");
-                for (u64 m = l; m <= i; m++) bnd[m] = rnm * std::fabs(bnd[m]);
-                l = i + 1;
-            }
-            cosort_ascending(j + 1, ritz.data(), bnd.data());
-            size_t ne = 0;
-            int rc = refine_bounds(&enough, endl, endr, ritz.data(), bnd.data(), j, tol, &ne);
-            if (rc) throw Error(rc, "error_bound: expected 'step' to be non-zero");
-            neig = ne;
-
+            analyze_T(j, rnm, tol, bet.data(), &enough, &neig);
             // should we stop?
-            if (neig < dims) {
-                if (neig == 0) {
-                    last = first + 9;
-                    intro = first;
-                } else {
-                    last = first + std::max<u64>(3, 1 + ((j - intro) * (dims - neig)) / neig);
-                }
-                last = std::min(last, iters);
-            } else {
-                enough = true;
-            }
-            enough = enough || first >= iters;
+            last = next_last(first, j, neig, &intro, &enough);
         }
         *neig_out = neig;
         return j;
     }
+
+    // lanso with the analyses of T overlapped (single GPU).  The main thread runs the steps one after the other and records,
+    // per finished step, the (rnm, tol) the sequential code would hand to an analysis there; the helper thread walks the
+    // batch boundaries exactly as the loop above does (same first / last / intro arithmetic), analysing T at a boundary as soon
+    // as that step has been taken, and raises `stop` when the reference would leave the loop.  Steps the main thread took
+    // beyond that boundary are discarded: they only ever wrote panel columns, alf / bet entries and r BEYOND the boundary
+    // (purge touches the current column and r), and the counters are put back to their values at the boundary.  Errors keep
+    // the reference's order: an exception of step s surfaces only if no earlier boundary stops or fails first.
+    struct Overlap {
+        std::mutex mu;
+        std::condition_variable cv;
+        // main -> helper
+        u64 done_step = 0;          // steps 1 .. done_step are complete
+        bool halted = false;        // the main thread takes no more steps: breakdown (`enough` inside a step), or an exception
+        u64 halt_first = 0;         // ... the step that was not taken
+        bool halt_is_error = false;
+        double halt_rnm = 0.0, halt_tol = 0.0;
+        std::exception_ptr main_exc;
+        u64 awaited = ~(u64)0;      // boundary step the helper is waiting for right now
+        // helper -> main
+        bool decided = false;
+        u64 j_final = 0, neig_final = 0;
+        std::exception_ptr helper_exc;
+        std::atomic<bool> stop{false};
+    };
+
+    u64 lanso_overlapped(double rnm, double tol, u64 *neig_out) {
+        Overlap ov;
+        std::vector<double> rnm_at(iters + 1, 0.0), tol_at(iters + 1, 0.0);
+        std::vector<svdlas2_profile> prof_at(iters + 1);
+        rnm_at[0] = rnm; tol_at[0] = tol; prof_at[0] = prof;
+
+        std::thread helper([&] {
+            try {
+                std::vector<double> betv(iters + 2, 0.0);
+                u64 first = 1, last = std::min(iters, std::max<u64>(dims, 8) + dims);
+                u64 j = 0, intro = 0, neig = 0;
+                bool enough = false;
+                while (!enough) {
+                    double a_rnm, a_tol;
+                    {
+                        std::unique_lock<std::mutex> lk(ov.mu);
+                        ov.awaited = last - 1;
+                        ov.cv.notify_all();
+                        ov.cv.wait(lk, [&] { return ov.done_step + 1 >= last || ov.halted; });
+                        ov.awaited = ~(u64)0;
+                        if (ov.done_step + 1 >= last) {
+                            j = last - 1;                       // the batch ran to its end
+                            a_rnm = rnm_at[j]; a_tol = tol_at[j];
+                        } else {
+                            if (ov.halt_is_error) std::rethrow_exception(ov.main_exc); // the batch would have thrown at that step
+                            enough = true;                      // lanczos_step left the batch early (:1262): j = steps - 1
+                            j = ov.halt_first - 1;
+                            a_rnm = ov.halt_rnm; a_tol = ov.halt_tol;
+                        }
+                    }
+                    first = j + 1;
+                    std::memcpy(betv.data(), bet.data(), (j + 1) * sizeof(double)); // final: steps <= j are complete
+                    betv[first] = a_rnm;                                              // bet[first] = rnm, :1971
+                    analyze_T(j, a_rnm, a_tol, betv.data(), &enough, &neig);
+                    last = next_last(first, j, neig, &intro, &enough);
+                }
+                std::lock_guard<std::mutex> lk(ov.mu);
+                ov.j_final = j; ov.neig_final = neig; ov.decided = true;
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(ov.mu);
+                ov.helper_exc = std::current_exception();
+                ov.decided = true;
+            }
+            ov.stop.store(true, std::memory_order_release);
+            ov.cv.notify_all();
+        });
+        // leaving by an exception that is not a step's own (allocation failure ...): release the helper before joining it
+        struct Joiner {
+            std::thread &t; Overlap &ov;
+            ~Joiner() {
+                if (!t.joinable()) return;
+                {
+                    std::lock_guard<std::mutex> lk(ov.mu);
+                    if (!ov.decided && !ov.halted) {
+                        ov.halted = true; ov.halt_is_error = true; ov.halt_first = ov.done_step + 1;
+                        ov.main_exc = std::make_exception_ptr(Error(SVDLAS2_ERR_CUDA, "solve abandoned"));
+                    }
+                }
+                ov.cv.notify_all();
+                t.join();
+            }
+        } joiner{helper, ov};
+
+        u64 ll = 0, j = 1;
+        bool enough = false;
+        spec_horizon = iters;
+        double step_s = 0.0; // running mean of a step's wall time
+        u64 nsteps = 0;
+        auto halt = [&](bool is_error) {
+            std::unique_lock<std::mutex> lk(ov.mu);
+            ov.halted = true; ov.halt_first = j; ov.halt_is_error = is_error; ov.halt_rnm = rnm; ov.halt_tol = tol;
+            if (is_error) ov.main_exc = std::current_exception();
+            ov.cv.notify_all();
+            ov.cv.wait(lk, [&] { return ov.decided; });
+        };
+        while (!ov.stop.load(std::memory_order_acquire)) {
+            if (j >= iters) { // every step a batch can ask for has been taken: the helper decides alone from here
+                std::unique_lock<std::mutex> lk(ov.mu);
+                ov.cv.wait(lk, [&] { return ov.decided; });
+                break;
+            }
+            const double ts0 = wall();
+            try {
+                if (rnm <= tol) rnm = 0.0;
+                lanczos_step(j, j + 1, &ll, &enough, &rnm, &tol);
+            } catch (...) {
+                halt(true);
+                break;
+            }
+            if (enough) { halt(false); break; } // breakdown: the step was not taken
+            step_s += (wall() - ts0 - step_s) / (double)(++nsteps);
+            rnm_at[j] = rnm; tol_at[j] = tol; prof_at[j] = prof;
+            bool at_boundary;
+            {
+                std::lock_guard<std::mutex> lk(ov.mu);
+                ov.done_step = j;
+                at_boundary = ov.awaited == j;
+            }
+            ov.cv.notify_all();
+            // A step that is long next to an analysis is not worth gambling: give the helper a third of a step's time to
+            // answer before the next step is launched (it usually says "stop" or "go on" within that).
+            if (at_boundary && step_s > 50e-6) {
+                std::unique_lock<std::mutex> lk(ov.mu);
+                ov.cv.wait_for(lk, std::chrono::duration<double>(0.3 * step_s),
+                               [&] { return ov.decided || (ov.awaited != ~(u64)0 && ov.awaited != j); });
+            }
+            j++;
+        }
+        helper.join();
+        if (ov.helper_exc) std::rethrow_exception(ov.helper_exc);
+        // the state the sequential loop would have ended with
+        const u64 jf = ov.j_final;
+        const double t_sync = prof.t_sync_wait;
+        const u64 launches = prof.n_kernel_launches, syncs = prof.n_host_syncs, h2d = prof.h2d_bytes;
+        if (!ov.halted || jf < ov.halt_first - 1 || ov.halt_is_error) {
+            prof = prof_at[jf];
+            bet[jf + 1] = rnm_at[jf];
+        } else {
+            bet[jf + 1] = ov.halt_rnm; // the batch that broke down: counters are already those of its last step
+        }
+        prof.t_sync_wait = t_sync; prof.n_kernel_launches = launches; prof.n_host_syncs = syncs; prof.h2d_bytes = h2d; // work really done
+        n_overshoot = ov.done_step > jf ? ov.done_step - jf : 0;
+        spec_col = ~(u64)0;
+        qused = std::min(qused, jf + 1);
+        *neig_out = ov.neig_final;
+        return jf;
+    }
+    u64 n_overshoot = 0;  // steps taken beyond the final boundary (lanso_overlapped)
+    u64 spec_horizon = 0; // lanso_overlapped calls lanczos_step one step at a time: the next step exists up to here
 
     // ---- ritvec (src/lib.rs:1767-1879) ----
     void ritvec(u64 steps, u64 neig, double kappa, svdlas2_result *res, double *t_imtql2) {
@@ -797,9 +974,10 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
         fprintf(stderr, "[svdlas2] lanso: %llu purge passes, %llu reorthogonalisation sweeps split over %d ranks\n",
                 (unsigned long long)sv.prof.n_purge_passes, (unsigned long long)sv.n_sharded_sweeps, op.comm->world());
     if (std::getenv("SVDLAS2_TRACE"))
-        fprintf(stderr, "[svdlas2] lanso: %.4f s, of which purge %.4f s (%llu passes, %llu stored vectors), analyses of T %.4f s, waiting "
-                        "for step scalars %.4f s\n", sv.prof.t_lanczos, sv.t_purge_host, (unsigned long long)sv.prof.n_purge_passes,
-                (unsigned long long)sv.prof.n_purge_vectors, sv.t_analysis_host, sv.prof.t_sync_wait);
+        fprintf(stderr, "[svdlas2] lanso: %.4f s, of which purge %.4f s (%llu passes, %llu stored vectors), analyses of T %.4f s%s, waiting "
+                        "for step scalars %.4f s; %llu steps taken beyond the final boundary\n", sv.prof.t_lanczos, sv.t_purge_host,
+                (unsigned long long)sv.prof.n_purge_passes, (unsigned long long)sv.prof.n_purge_vectors, sv.t_analysis_host,
+                op.comm ? "" : " (on the helper thread, next to the steps)", sv.prof.t_sync_wait, (unsigned long long)sv.n_overshoot);
 
     kappa = std::max(std::fabs(kappa), eps34()); // :627
     dg.kappa = kappa;

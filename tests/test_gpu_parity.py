@@ -649,3 +649,36 @@ def test_ql_replay_on_the_gpu_is_bit_identical(las2, n, seed, clustered):
         assert np.array_equal(z1, z0), f"variant {variant}: {np.count_nonzero(z1 != z0)} entries differ"
         times[variant] = ms.value
     print(f"[ql replay] n={n} rotations={nrot.value}: one warp {times[0]:.3f} ms, pipeline {times[1]:.3f} ms")
+
+
+def test_overlapped_analysis_equals_the_sequential_schedule(las2, oracle, monkeypatch):
+    """lanso with the analyses of T (reference src/lib.rs:1975-2010) on a helper thread next to the Lanczos steps: the
+    recurrence does not depend on the analyses, only its stopping point does, so the result must be BIT-identical to the
+    sequential schedule -- same stopping step, same trace (incl. bet[steps + 1] = rnm), same counters -- however many steps
+    were taken beyond the final boundary; covers early breakdown (identity: restart fails), an exhausted iteration budget,
+    purge-heavy runs and the error order (NaN entry -> ImtqlbError from the analysis, not from a later step)."""
+    from svdlibrs_b200 import synthetic
+    cases = [(synthetic.make("cfg1", scale=0.2)[0], 12, 0), (synthetic.make("cfg2", scale=0.02)[0], 30, 0),
+             (synthetic.make("cfg3", scale=0.01)[0], 15, 0), (sp.random(400, 300, density=0.05, format="csr", random_state=3), 10, 0),
+             (sp.random(300, 200, density=0.1, format="csc", random_state=4), 40, 60),  # iterations cap reached
+             (sp.identity(3, format="csc"), 0, 0), (sp.csr_matrix(GOLDEN_M), 0, 0)]
+    for A, dims, iters in cases:
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("SVDLAS2_OVERLAP_ANALYSIS", mode)
+            d = dims or min(A.shape)
+            out[mode] = las2.svdLAS2(A, d, iters, [-1e-30, 1e-30], 1e-6, 12345) if iters else las2.svd_dim_seed(A, d, 12345)
+        a, b = out["0"], out["1"]
+        assert a.diagnostics == b.diagnostics
+        assert np.array_equal(a.s, b.s) and np.array_equal(a.ut, b.ut) and np.array_equal(a.vt, b.vt)
+        for k in ("alf", "bet", "ritz", "bnd"):
+            assert np.array_equal(a.trace[k], b.trace[k], equal_nan=True), k
+        for k in ("n_opb", "n_spmv", "n_purge_fired", "n_purge_passes", "n_purge_vectors", "n_restarts"):
+            assert a.profile[k] == b.profile[k], k
+    monkeypatch.setenv("SVDLAS2_OVERLAP_ANALYSIS", "1")
+    assert_svd_parity(out["1"], oracle.svd_dim_seed(sp.csr_matrix(GOLDEN_M), 3, 12345))
+    B = sp.random(60, 40, density=0.3, format="csr", random_state=1)
+    B.data[5] = np.nan
+    with pytest.raises(las2.SvdLibError) as ei:
+        las2.svd_dim_seed(B, 5, 12345)
+    assert ei.value.kind == "ImtqlbError"
