@@ -508,11 +508,14 @@ struct Solver {
         stpone(seed, &rnm, &tol);
         eta[0] = eps1;
         oldeta[0] = eps1;
-        // One GPU: the Lanczos recurrence does not depend on the analyses (they only decide where it STOPS), so the analyses
-        // run on a helper thread while the steps go on.  Sharded runs keep the sequential schedule: every rank must launch the
-        // same collectives, and how far a rank runs ahead of its helper depends on timing.
+        // The Lanczos recurrence does not depend on the analyses (they only decide where it STOPS), so on one GPU they can run
+        // on a helper thread while the steps go on (lanso_overlapped, SVDLAS2_OVERLAP_ANALYSIS=1).  Opt-in: the cost of an
+        // analysis grows with j^2, so the LAST one dominates their sum and nothing useful can run next to it -- measured
+        // (profiles/r2y_overlapped_analysis.md): cfg 1 unchanged, cfg 5 slower (114 discarded steps with their purges, and two
+        // busy host threads inside the box's CPU quota).  Sharded runs always keep the sequential schedule: every rank must
+        // launch the same collectives, and how far a rank runs ahead of its helper depends on timing.
         const char *e = std::getenv("SVDLAS2_OVERLAP_ANALYSIS");
-        if (!op.comm && !(e && e[0] == '0')) return lanso_overlapped(rnm, tol, neig_out);
+        if (!op.comm && e && e[0] == '1') return lanso_overlapped(rnm, tol, neig_out);
         u64 ll = 0, first = 1;
         u64 last = std::min(iters, std::max<u64>(dims, 8) + dims);
         bool enough = false;
@@ -977,7 +980,7 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
         fprintf(stderr, "[svdlas2] lanso: %.4f s, of which purge %.4f s (%llu passes, %llu stored vectors), analyses of T %.4f s%s, waiting "
                         "for step scalars %.4f s; %llu steps taken beyond the final boundary\n", sv.prof.t_lanczos, sv.t_purge_host,
                 (unsigned long long)sv.prof.n_purge_passes, (unsigned long long)sv.prof.n_purge_vectors, sv.t_analysis_host,
-                op.comm ? "" : " (on the helper thread, next to the steps)", sv.prof.t_sync_wait, (unsigned long long)sv.n_overshoot);
+                sv.spec_horizon ? " (on the helper thread, next to the steps)" : "", sv.prof.t_sync_wait, (unsigned long long)sv.n_overshoot);
 
     kappa = std::max(std::fabs(kappa), eps34()); // :627
     dg.kappa = kappa;
