@@ -1,2 +1,2 @@
-(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --durations=6 -k "overlapped or step_chain or errors or error_codes or cfg1_full or identity or golden or iterations_and_kappa or recorded or reusable or random_sparse" > gpurun_out/r2y_pytest_overlap.log 2>&1; echo pytest rc=$? >> gpurun_out/r2y_pytest_overlap.log); tail -15 gpurun_out/r2y_pytest_overlap.log
-for w in cfg1 cfg5 cfg2; do for ov in 0 1; do echo "== $w overlap=$ov"; SVDLAS2_OVERLAP_ANALYSIS=$ov SVDLAS2_TRACE=1 timeout 300 python scripts/solve_profile.py --workload $w --reps 3 2>&1 | grep -E "wall|lanso" | tail -2 | cut -c1-460; done; done
+for w in cfg2 cfg5; do echo "== $w ritvec variance"; SVDLAS2_TRACE=1 timeout 300 python scripts/solve_profile.py --workload $w --reps 6 > gpurun_out/r2z_trace_$w.log 2>&1; grep -E "^\{" gpurun_out/r2z_trace_$w.log | cut -c1-330; done
+bash scripts/ncu_r2v.sh > gpurun_out/r2v_ncu_call.log 2>&1; tail -12 gpurun_out/r2v_ncu_call.log

@@ -171,6 +171,89 @@ k_panel_update(const double *__restrict__ Q, u64 ld, u32 col0, u32 ncols, const 
     }
 }
 
+// The same update for SHORT vectors.  With one double2 per thread a vector of 10,000 rows is 39 CTAs of the kernel above, and
+// the ~8 loads a thread keeps in flight are far too few bytes for the memory latency: 85 us per sweep of ~400 columns at cfg 1
+// (profiles/r2v_launches_cfg1_summary.csv; the compiler does not hoist more loads whatever the unroll factor).  Here every
+// thread streams its element of the next 24-48 columns into shared memory with cp.async (4 stages of 16 or 8 columns, no
+// registers held, no barrier: a thread only ever reads what it copied itself), CTAs of 32 or 64 threads spread the rows over
+// two to four times as many SMs, and the arithmetic -- order included -- is unchanged.
+constexpr int kDeepStages = 4; // x (16 columns x 32 threads) or (8 columns x 64 threads) x 16 B = 32 KB of static shared memory
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NRHS, int kDeepThreads, int kDeepCols>
+__global__ void __launch_bounds__(kDeepThreads)
+k_panel_update_deep(const double *__restrict__ Q, u64 ld, u32 col0, u32 ncols, const double *__restrict__ coeffs,
+                    double *__restrict__ a, double *__restrict__ b, double *__restrict__ dot_parts, u64 i0, u64 i1) {
+    __shared__ double sc[NRHS][kUpdChunk];
+    __shared__ double sm[2];
+    __shared__ __align__(16) double2 stage[kDeepStages][kDeepCols][kDeepThreads];
+    const u64 i = i0 + (u64)blockIdx.x * kDeepThreads + threadIdx.x;
+    const bool live = i < i1;
+    double2 av = make_double2(0.0, 0.0), bv = make_double2(0.0, 0.0);
+    if (live) {
+        av = reinterpret_cast<double2 *>(a)[i];
+        if (NRHS > 1) bv = reinterpret_cast<double2 *>(b)[i];
+    }
+    const u64 ld2 = ld / 2;
+    for (u32 c0 = 0; c0 < ncols; c0 += kUpdChunk) {
+        const u32 nc = min((u32)kUpdChunk, ncols - c0);
+        __syncthreads();
+        for (u32 k = threadIdx.x; k < nc; k += kDeepThreads) {
+            sc[0][k] = -coeffs[c0 + k];
+            if (NRHS > 1) sc[1][k] = -coeffs[ncols + c0 + k];
+        }
+        __syncthreads();
+        if (!live) continue;
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(Q + (u64)(col0 + c0) * ld) + i;
+        const u32 ngroups = (nc + kDeepCols - 1) / kDeepCols;
+        auto issue = [&](u32 g) { // columns [g * 16, g * 16 + 16) of this chunk into slot g % stages (always one commit)
+            if (g < ngroups) {
+                const u32 k0 = g * kDeepCols, kn = min((u32)kDeepCols, nc - k0);
+                for (u32 u = 0; u < kn; u++) cp_async16(&stage[g % kDeepStages][u][threadIdx.x], q + (u64)(k0 + u) * ld2);
+            }
+            cp_async_commit();
+        };
+        for (u32 g = 0; g + 1 < (u32)kDeepStages; g++) issue(g);
+        for (u32 g = 0; g < ngroups; g++) {
+            issue(g + kDeepStages - 1);
+            cp_async_wait<kDeepStages - 1>(); // group g has landed
+            const u32 k0 = g * kDeepCols, kn = min((u32)kDeepCols, nc - k0);
+#pragma unroll 4
+            for (u32 u = 0; u < kn; u++) {
+                const double2 qv = stage[g % kDeepStages][u][threadIdx.x];
+                const u32 k = k0 + u;
+                av.x = __dadd_rn(av.x, __dmul_rn(sc[0][k], qv.x));
+                av.y = __dadd_rn(av.y, __dmul_rn(sc[0][k], qv.y));
+                if (NRHS > 1) {
+                    bv.x = __dadd_rn(bv.x, __dmul_rn(sc[1][k], qv.x));
+                    bv.y = __dadd_rn(bv.y, __dmul_rn(sc[1][k], qv.y));
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+    double acc = 0.0;
+    if (live) {
+        reinterpret_cast<double2 *>(a)[i] = av;
+        if (NRHS > 1) {
+            reinterpret_cast<double2 *>(b)[i] = bv;
+            acc = fma(av.x, bv.x, 0.0);
+            acc = fma(av.y, bv.y, acc);
+        }
+    }
+    if (NRHS > 1 && dot_parts) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        acc = warp_sum(acc);
+        if (lane == 0) sm[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) dot_parts[blockIdx.x] = kDeepThreads > 32 ? sm[0] + sm[1] : sm[0];
+    }
+}
+
 // abs_a[cta] / abs_b[cta] = sum |coeff| over the CTA's 128 columns (sharded sweep: the coefficients are complete only
 // after the all-reduce, so the sums cannot come out of k_panel_reduce)
 template <int NRHS>
@@ -382,7 +465,11 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
     const u32 nred = cdiv(ncols, 128);
     if (nred > (u32)kMaxParts) throw Error(SVDLAS2_ERR_INVALID_ARGUMENT, "panel_cgs2: too many columns");
     dim3 grid(nblocks, cs);
-    const u32 ugrid = cdiv(i1 - i0, kUpdThreads);
+    // short vectors (fewer than two CTAs of the plain kernel per SM): the cp.async-pipelined sibling on CTAs of 64 threads
+    static const bool deep_on = [] { const char *e = std::getenv("SVDLAS2_PANEL_DEEP"); return !(e && e[0] == '0'); }();
+    const bool deep = deep_on && cdiv(i1 - i0, kUpdThreads) < 2u * (u32)kNumSMs;
+    const u32 deep_threads = (i1 - i0) <= 32u * (u32)kMaxParts ? 32u : 64u; // (one dot partial per CTA, at most kMaxParts of them)
+    const u32 ugrid = cdiv(i1 - i0, deep ? deep_threads : (u32)kUpdThreads);
     const int nrhs = b ? 2 : 1;
     if (ev_begin) LAS2_CUDA(cudaEventRecord(ev_begin, s)); // tuning hook (svdlas2_test_time_panel)
     // ---- coefficients ----
@@ -411,7 +498,9 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
             if (work.dotparts.size() < ugrid) work.dotparts.alloc(ugrid);
             dp = work.dotparts;
         }
-        if (ugrid) k_panel_update<2><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, b, dp, i0, i1);
+        if (ugrid && deep && deep_threads == 32) k_panel_update_deep<2, 32, 16><<<ugrid, 32, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, b, dp, i0, i1);
+        else if (ugrid && deep) k_panel_update_deep<2, 64, 8><<<ugrid, 64, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, b, dp, i0, i1);
+        else if (ugrid) k_panel_update<2><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, b, dp, i0, i1);
         if (launches) *launches += 1;
         if (dot_out && !shard) {
             if (ugrid > (u32)kMaxParts) {
@@ -425,7 +514,9 @@ void panel_cgs2(const double *Q, u64 ld, u64 n, u32 col0, u32 ncols, double *a, 
             }
         }
     } else {
-        if (ugrid) k_panel_update<1><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, nullptr, nullptr, i0, i1);
+        if (ugrid && deep && deep_threads == 32) k_panel_update_deep<1, 32, 16><<<ugrid, 32, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, nullptr, nullptr, i0, i1);
+        else if (ugrid && deep) k_panel_update_deep<1, 64, 8><<<ugrid, 64, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, nullptr, nullptr, i0, i1);
+        else if (ugrid) k_panel_update<1><<<ugrid, kUpdThreads, 0, s>>>(Q, ld, col0, ncols, work.coeffs, a, nullptr, nullptr, i0, i1);
         if (launches) *launches += 1;
     }
     if (shard) {
