@@ -153,8 +153,11 @@ struct Solver {
 
     double *q(u64 j) { return Q.get() + j * ld; }
 
+    double t_grow = 0.0; // SVDLAS2_TRACE: host time spent growing the panel
     void ensure_cols(u64 need) {
         if (need <= qcap) return;
+        const double tg0 = wall();
+        struct TG { double &acc; double t0; ~TG() { acc += wall() - t0; } } tg{t_grow, tg0};
         u64 cap = qcap ? qcap * 2 : std::max<u64>(64, 2 * (std::max<u64>(dims, 8) + dims));
         if (cap < need) cap = need;
         if (cap > iters + 1) cap = std::max(need, iters + 1);
@@ -968,6 +971,7 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
     struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev_guard{ev_begin, ev_end};
     LAS2_CUDA(cudaEventRecord(ev_begin, op.stream));
 
+    if (std::getenv("SVDLAS2_TRACE")) { double z[6]; device_alloc_stats(z, true); }
     Solver sv(op, dimensions, iterations);
     u64 neig = 0;
     const double tl0 = wall();
@@ -978,9 +982,9 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
                 (unsigned long long)sv.prof.n_purge_passes, (unsigned long long)sv.n_sharded_sweeps, op.comm->world());
     if (std::getenv("SVDLAS2_TRACE"))
         fprintf(stderr, "[svdlas2] lanso: %.4f s, of which purge %.4f s (%llu passes, %llu stored vectors), analyses of T %.4f s%s, waiting "
-                        "for step scalars %.4f s; %llu steps taken beyond the final boundary\n", sv.prof.t_lanczos, sv.t_purge_host,
+                        "for step scalars %.4f s, growing the panel %.4f s; %llu steps taken beyond the final boundary\n", sv.prof.t_lanczos, sv.t_purge_host,
                 (unsigned long long)sv.prof.n_purge_passes, (unsigned long long)sv.prof.n_purge_vectors, sv.t_analysis_host,
-                sv.spec_horizon ? " (on the helper thread, next to the steps)" : "", sv.prof.t_sync_wait, (unsigned long long)sv.n_overshoot);
+                sv.spec_horizon ? " (on the helper thread, next to the steps)" : "", sv.prof.t_sync_wait, sv.t_grow, (unsigned long long)sv.n_overshoot);
 
     kappa = std::max(std::fabs(kappa), eps34()); // :627
     dg.kappa = kappa;
@@ -1026,6 +1030,12 @@ void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interv
     sv.prof.h2d_bytes += op.upload.h2d_bytes;
     sv.prof.opb_algorithmic_bytes = op.opb_bytes();
     sv.prof.t_total = wall() - t0;
+    if (std::getenv("SVDLAS2_TRACE")) {
+        double a[6];
+        device_alloc_stats(a, false);
+        fprintf(stderr, "[svdlas2] solve: %.4f s; device allocator: %.0f allocations %.4f s (longest %.4f s), %.0f releases %.4f s (longest %.4f s)\n",
+                sv.prof.t_total, a[2], a[0], a[1], a[5], a[3], a[4]);
+    }
     res->profile = sv.prof;
 }
 

@@ -1,8 +1,13 @@
 // util.cu -- device memory pool behind DevBuf (see util.cuh).
 #include "util.cuh"
 
+#include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
+#include <unordered_map>
+#include <vector>
 
 namespace las2 {
 
@@ -15,7 +20,19 @@ struct PoolState {
     cudaMemPool_t pool[kMaxDevices] = {};
     bool ready[kMaxDevices] = {};
     bool legacy = false; // SVDLAS2_DEVICE_POOL=0: plain cudaMalloc / cudaFree
+    // Large blocks (>= kBigBlock) are not handed back to the stream-ordered pool but parked here and re-issued to the next
+    // request of (nearly) the same size.  Why: the pool keeps its memory (release threshold lifted), yet every few solves a
+    // request of the same 0.8 GB that was freed a moment ago came back after 0.1-0.43 s -- the pool had carved smaller
+    // allocations out of the freed range and mapped fresh physical memory for the big one (40 solves of cfg 2: six of them
+    // 2-5 x slower for this one allocation alone, profiles/r2ab_allocator_outliers.md).  A solve repeats its sequence of
+    // sizes exactly, so an exact-fit list makes the reuse deterministic.
+    struct Parked { void *p; size_t cap; };
+    std::vector<Parked> parked[kMaxDevices];
+    size_t parked_bytes[kMaxDevices] = {};
+    std::unordered_map<void *, size_t> big_live; // blocks >= kBigBlock handed out: pointer -> capacity
+    size_t park_limit[kMaxDevices] = {};         // bytes worth keeping parked (a third of the device; SVDLAS2_DEVICE_PARK_MB)
 };
+constexpr size_t kBigBlock = (size_t)8 << 20;
 
 PoolState &state() {
     static PoolState *s = [] {
@@ -48,44 +65,150 @@ cudaStream_t alloc_stream(int dev) {
     return S.stream[dev];
 }
 
+// SVDLAS2_TRACE bookkeeping: where a host thread loses time inside the allocator (device_alloc_stats)
+std::atomic<uint64_t> g_alloc_ns{0}, g_alloc_max_ns{0}, g_alloc_calls{0}, g_free_ns{0}, g_free_max_ns{0}, g_free_calls{0};
+struct AllocTimer {
+    std::atomic<uint64_t> &sum, &mx, &calls;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~AllocTimer() {
+        const uint64_t ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        sum += ns; calls += 1;
+        uint64_t cur = mx.load();
+        while (ns > cur && !mx.compare_exchange_weak(cur, ns)) {}
+    }
+};
+
+} // namespace
+
+void device_alloc_stats(double out[6], bool reset) {
+    out[0] = g_alloc_ns.load() * 1e-9; out[1] = g_alloc_max_ns.load() * 1e-9; out[2] = (double)g_alloc_calls.load();
+    out[3] = g_free_ns.load() * 1e-9; out[4] = g_free_max_ns.load() * 1e-9; out[5] = (double)g_free_calls.load();
+    if (reset) { g_alloc_ns = 0; g_alloc_max_ns = 0; g_alloc_calls = 0; g_free_ns = 0; g_free_max_ns = 0; g_free_calls = 0; }
+}
+
+namespace {
+
+void *pool_alloc(int dev, size_t bytes, cudaError_t *err) {
+    void *p = nullptr;
+    cudaStream_t as = alloc_stream(dev);
+    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, state().pool[dev], as);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(as);
+    if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+    *err = e;
+    return p;
+}
+
+void pool_free(int dev, void *p) {
+    cudaStream_t as = nullptr;
+    try { as = alloc_stream(dev); } catch (...) { cudaFree(p); return; }
+    if (cudaFreeAsync(p, as) != cudaSuccess) { cudaGetLastError(); cudaFree(p); }
+}
+
+// hands every parked block of the device back to the pool (the caller has made sure the device is idle)
+void unpark_all(int dev) {
+    PoolState &S = state();
+    std::vector<PoolState::Parked> take;
+    {
+        std::lock_guard<std::mutex> lk(S.mu);
+        take.swap(S.parked[dev]);
+        S.parked_bytes[dev] = 0;
+    }
+    for (auto &b : take) pool_free(dev, b.p);
+}
+
 } // namespace
 
 void *device_alloc(size_t bytes) {
     void *p = nullptr;
     if (bytes == 0) return nullptr;
+    AllocTimer timer{g_alloc_ns, g_alloc_max_ns, g_alloc_calls};
     cudaError_t e;
     int dev = 0;
     LAS2_CUDA(cudaGetDevice(&dev));
     if (state().legacy || dev >= kMaxDevices) {
         e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) cudaGetLastError();
     } else {
-        cudaStream_t as = alloc_stream(dev);
-        e = cudaMallocFromPoolAsync(&p, bytes, state().pool[dev], as);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(as);
+        PoolState &S = state();
+        if (bytes >= kBigBlock) {
+            // smallest parked block that fits without wasting more than 1/8 of it
+            std::lock_guard<std::mutex> lk(S.mu);
+            auto &v = S.parked[dev];
+            size_t best = v.size();
+            for (size_t i = 0; i < v.size(); i++)
+                if (v[i].cap >= bytes && v[i].cap - bytes <= bytes / 8 && (best == v.size() || v[i].cap < v[best].cap)) best = i;
+            if (best != v.size()) {
+                const PoolState::Parked b = v[best];
+                v.erase(v.begin() + (long)best);
+                S.parked_bytes[dev] -= b.cap;
+                S.big_live[b.p] = b.cap;
+                return b.p;
+            }
+        }
+        p = pool_alloc(dev, bytes, &e);
+        if (!p) { // out of memory with blocks parked: give them back and try once more
+            cudaDeviceSynchronize();
+            unpark_all(dev);
+            cudaMemPoolTrimTo(S.pool[dev], 0);
+            p = pool_alloc(dev, bytes, &e);
+        }
+        if (p && bytes >= kBigBlock) {
+            std::lock_guard<std::mutex> lk(S.mu);
+            S.big_live[p] = bytes;
+        }
     }
-    if (e != cudaSuccess) {
-        cudaGetLastError();
+    if (!p)
         throw Error(SVDLAS2_ERR_ALLOC, "device allocation of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
-    }
     return p;
 }
 
 void device_free(void *p) {
     if (!p) return;
+    AllocTimer timer{g_free_ns, g_free_max_ns, g_free_calls};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || state().legacy || dev >= kMaxDevices) { cudaFree(p); return; }
     // like cudaFree: nothing that may still touch the buffer is in flight once the device is idle
     cudaDeviceSynchronize();
-    cudaStream_t as = nullptr;
-    try { as = alloc_stream(dev); } catch (...) { cudaFree(p); return; }
-    if (cudaFreeAsync(p, as) != cudaSuccess) { cudaGetLastError(); cudaFree(p); }
+    PoolState &S = state();
+    std::vector<PoolState::Parked> evict; // handed back to the pool outside the lock
+    {
+        std::lock_guard<std::mutex> lk(S.mu);
+        auto it = S.big_live.find(p);
+        if (it != S.big_live.end()) {
+            const size_t cap = it->second;
+            S.big_live.erase(it);
+            if (S.park_limit[dev] == 0) {
+                size_t free_b = 0, total_b = 0;
+                const char *e = std::getenv("SVDLAS2_DEVICE_PARK_MB");
+                if (e) S.park_limit[dev] = ((size_t)std::strtoull(e, nullptr, 10) << 20) | 1;
+                else S.park_limit[dev] = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 3 : (size_t)16 << 30) | 1;
+            }
+            if (cap <= S.park_limit[dev]) {
+                // make room: the oldest parked blocks go back to the pool first
+                auto &v = S.parked[dev];
+                while (S.parked_bytes[dev] + cap > S.park_limit[dev] && !v.empty()) {
+                    evict.push_back(v.front());
+                    S.parked_bytes[dev] -= v.front().cap;
+                    v.erase(v.begin());
+                }
+                v.push_back(PoolState::Parked{p, cap});
+                S.parked_bytes[dev] += cap;
+                p = nullptr;
+            }
+        }
+    }
+    for (auto &b : evict) pool_free(dev, b.p);
+    if (p) pool_free(dev, p);
 }
 
 void device_pool_trim() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return;
     cudaDeviceSynchronize();
-    if (dev < kMaxDevices && state().ready[dev]) cudaMemPoolTrimTo(state().pool[dev], 0);
+    if (dev < kMaxDevices && state().ready[dev]) {
+        unpark_all(dev);
+        cudaMemPoolTrimTo(state().pool[dev], 0);
+    }
 }
 
 } // namespace las2

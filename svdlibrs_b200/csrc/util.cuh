@@ -45,6 +45,9 @@ struct Error : std::runtime_error {
 void *device_alloc(size_t bytes);
 void device_free(void *p);
 void device_pool_trim(); // give cached device memory back to the driver
+// host time spent inside device_alloc / device_free since the last reset: {alloc total s, alloc max s, alloc calls, free total s,
+// free max s, free calls} (SVDLAS2_TRACE)
+void device_alloc_stats(double out[6], bool reset);
 
 template <typename T>
 class DevBuf {
