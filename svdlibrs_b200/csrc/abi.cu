@@ -2,6 +2,7 @@
 // point maps las2::Error (and anything else) to a status code and a thread-local message.
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
@@ -77,6 +78,12 @@ Operator *create_operator(int format, u64 nrows, u64 ncols, u64 nnz, const u64 *
     HostSparse A{format, nrows, ncols, nnz, a, b, values};
     build_operator(A, op->transposed, op->stream, op->B, op->BT, op->upload, op->relabel);
     op->t_upload = wall_now() - t0;
+    if (std::getenv("SVDLAS2_TRACE")) {
+        double a[6];
+        device_alloc_stats(a, true);
+        fprintf(stderr, "[svdlas2] upload: %.4f s; device allocator: %.0f allocations %.4f s (longest %.4f s), %.0f releases %.4f s (longest %.4f s)\n",
+                op->t_upload, a[2], a[0], a[1], a[5], a[3], a[4]);
+    }
     return op.release();
 }
 

@@ -25,13 +25,19 @@ struct PoolState {
     // request of the same 0.8 GB that was freed a moment ago came back after 0.1-0.43 s -- the pool had carved smaller
     // allocations out of the freed range and mapped fresh physical memory for the big one (40 solves of cfg 2: six of them
     // 2-5 x slower for this one allocation alone, profiles/r2ab_allocator_outliers.md).  A solve repeats its sequence of
-    // sizes exactly, so an exact-fit list makes the reuse deterministic.
-    struct Parked { void *p; size_t cap; };
+    // sizes exactly, so an exact-fit list makes the reuse deterministic.  svdlas2_trim_caches() and an allocation failure
+    // release everything that is parked.
+    struct Parked { void *p; size_t cap; uint64_t tick; };
     std::vector<Parked> parked[kMaxDevices];
     size_t parked_bytes[kMaxDevices] = {};
     std::unordered_map<void *, size_t> big_live; // blocks >= kBigBlock handed out: pointer -> capacity
-    size_t park_limit[kMaxDevices] = {};         // bytes worth keeping parked (a third of the device; SVDLAS2_DEVICE_PARK_MB)
+    // bytes worth keeping parked: unlimited by default -- the pool these blocks would otherwise return to keeps its memory
+    // as well (release threshold lifted), so parking adds no footprint; SVDLAS2_DEVICE_PARK_MB caps it.  A cap makes a cycle
+    // of requests larger than it thrash (oldest out first), which is what the e2e call of cfg 4 did with a third of the device.
+    size_t park_limit[kMaxDevices] = {};
+    uint64_t tick = 0;                           // big requests so far: parked blocks nobody asked for in kParkAge requests go back
 };
+constexpr uint64_t kParkAge = 4096;
 constexpr size_t kBigBlock = (size_t)8 << 20;
 
 PoolState &state() {
@@ -142,8 +148,10 @@ void *device_alloc(size_t bytes) {
                 v.erase(v.begin() + (long)best);
                 S.parked_bytes[dev] -= b.cap;
                 S.big_live[b.p] = b.cap;
+                S.tick++;
                 return b.p;
             }
+            S.tick++;
         }
         p = pool_alloc(dev, bytes, &e);
         if (!p) { // out of memory with blocks parked: give them back and try once more
@@ -178,20 +186,18 @@ void device_free(void *p) {
             const size_t cap = it->second;
             S.big_live.erase(it);
             if (S.park_limit[dev] == 0) {
-                size_t free_b = 0, total_b = 0;
                 const char *e = std::getenv("SVDLAS2_DEVICE_PARK_MB");
-                if (e) S.park_limit[dev] = ((size_t)std::strtoull(e, nullptr, 10) << 20) | 1;
-                else S.park_limit[dev] = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 3 : (size_t)16 << 30) | 1;
+                S.park_limit[dev] = e ? (((size_t)std::strtoull(e, nullptr, 10) << 20) | 1) : ~(size_t)0;
             }
             if (cap <= S.park_limit[dev]) {
                 // make room: the oldest parked blocks go back to the pool first
                 auto &v = S.parked[dev];
-                while (S.parked_bytes[dev] + cap > S.park_limit[dev] && !v.empty()) {
+                while (!v.empty() && (S.parked_bytes[dev] > S.park_limit[dev] - cap || S.tick - v.front().tick > kParkAge)) {
                     evict.push_back(v.front());
                     S.parked_bytes[dev] -= v.front().cap;
                     v.erase(v.begin());
                 }
-                v.push_back(PoolState::Parked{p, cap});
+                v.push_back(PoolState::Parked{p, cap, S.tick});
                 S.parked_bytes[dev] += cap;
                 p = nullptr;
             }
