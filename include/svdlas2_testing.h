@@ -55,6 +55,11 @@ SVDLAS2_API int svdlas2_test_time_ritz(uint64_t n, uint32_t js, uint32_t d, int 
  * replay incl. the upload of the plan (reps >= 2). */
 SVDLAS2_API int svdlas2_test_ql_replay(uint64_t n, double *d, double *e, double *z, int variant, int reps, int device, double *ms,
                                        uint64_t *n_rotations);
+/* GPU test hook for the device allocator behind every buffer of the library (util.cu): large blocks are parked on release and
+ * re-issued by exact fit; an allocation that does not fit next to what is parked gives the parked blocks back and succeeds.
+ * out[0] = bytes parked after releasing a block of 30 % of the free memory, out[1] = 1 when a slightly smaller request got that very
+ * block back, out[2] = 1 when a request of 80 % of the free memory then succeeded, out[3] = bytes parked after the final trim (0). */
+SVDLAS2_API int svdlas2_test_device_parking(int device, double out[4]);
 /* How the upload laid the operator out: out[0] = 1 when the N side was relabelled by popularity, out[1] = share of B's column
  * indices inside the shared-memory prefix (hot_fraction), out[2] = size of that prefix, out[3] / out[4] = mode of B's / B''s
  * first stream and out[5] of B''s second one (-1 none, 0 plain, 1 plain + hot prefix, 2 slab-local, 3 wide slabs),

@@ -427,6 +427,33 @@ int svdlas2_test_ql_replay(uint64_t n, double *d, double *e, double *z, int vari
     });
 }
 
+int svdlas2_test_device_parking(int device, double out[4]) {
+    if (!out) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        if (device >= 0) LAS2_CUDA(cudaSetDevice(device));
+        device_pool_trim();
+        size_t free_b = 0, total_b = 0;
+        LAS2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t small = free_b / 10 * 3, large = free_b / 10 * 8; // together more than the device has
+        double st[2];
+        void *a = device_alloc(small);
+        LAS2_CUDA(cudaMemset(a, 0, 1 << 20));
+        device_free(a);
+        device_parked_stats(st);
+        out[0] = st[1];
+        void *b = device_alloc(small - small / 16); // fits the parked block with less than 1/8 of slack
+        out[1] = b == a ? 1.0 : 0.0;
+        device_free(b);
+        void *c = device_alloc(large); // only possible once the parked block has gone back to the driver
+        LAS2_CUDA(cudaMemset(c, 0, 1 << 20));
+        out[2] = c ? 1.0 : 0.0;
+        device_free(c);
+        device_pool_trim();
+        device_parked_stats(st);
+        out[3] = st[1];
+    });
+}
+
 int svdlas2_test_operator_layout(const svdlas2_operator *op_, double out[8]) {
     const Operator *op = reinterpret_cast<const Operator *>(op_);
     if (!op || !out) return fail(SVDLAS2_ERR_INVALID_ARGUMENT, "null argument");

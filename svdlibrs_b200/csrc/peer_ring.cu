@@ -188,6 +188,7 @@ PeerRing *PeerRing::create(Comm *comm, u64 n_doubles) {
     const size_t bytes = block_bytes(n_doubles);
     // (a failure on one rank must not leave the others waiting in the exchange below: it becomes part of the agreement)
     cudaError_t e = cudaMalloc(&R->base, bytes);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); device_pool_trim(); e = cudaMalloc(&R->base, bytes); } // parked / pooled blocks in the way
     if (e == cudaSuccess) e = cudaMemset(R->base, 0, bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaIpcMemHandle_t mine;

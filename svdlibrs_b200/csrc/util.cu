@@ -86,6 +86,16 @@ struct AllocTimer {
 
 } // namespace
 
+void device_parked_stats(double out[2]) {
+    int dev = 0;
+    out[0] = out[1] = 0.0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= kMaxDevices) return;
+    PoolState &S = state();
+    std::lock_guard<std::mutex> lk(S.mu);
+    out[0] = (double)S.parked[dev].size();
+    out[1] = (double)S.parked_bytes[dev];
+}
+
 void device_alloc_stats(double out[6], bool reset) {
     out[0] = g_alloc_ns.load() * 1e-9; out[1] = g_alloc_max_ns.load() * 1e-9; out[2] = (double)g_alloc_calls.load();
     out[3] = g_free_ns.load() * 1e-9; out[4] = g_free_max_ns.load() * 1e-9; out[5] = (double)g_free_calls.load();
@@ -124,6 +134,8 @@ void unpark_all(int dev) {
 
 } // namespace
 
+void device_pool_trim();
+
 void *device_alloc(size_t bytes) {
     void *p = nullptr;
     if (bytes == 0) return nullptr;
@@ -154,10 +166,8 @@ void *device_alloc(size_t bytes) {
             S.tick++;
         }
         p = pool_alloc(dev, bytes, &e);
-        if (!p) { // out of memory with blocks parked: give them back and try once more
-            cudaDeviceSynchronize();
-            unpark_all(dev);
-            cudaMemPoolTrimTo(S.pool[dev], 0);
+        if (!p) { // out of memory with blocks parked: give them back to the driver and try once more
+            device_pool_trim();
             p = pool_alloc(dev, bytes, &e);
         }
         if (p && bytes >= kBigBlock) {
@@ -213,6 +223,7 @@ void device_pool_trim() {
     cudaDeviceSynchronize();
     if (dev < kMaxDevices && state().ready[dev]) {
         unpark_all(dev);
+        cudaStreamSynchronize(state().stream[dev]); // the releases above are ordered on the allocation stream
         cudaMemPoolTrimTo(state().pool[dev], 0);
     }
 }

@@ -48,6 +48,8 @@ void device_pool_trim(); // give cached device memory back to the driver
 // host time spent inside device_alloc / device_free since the last reset: {alloc total s, alloc max s, alloc calls, free total s,
 // free max s, free calls} (SVDLAS2_TRACE)
 void device_alloc_stats(double out[6], bool reset);
+// {number of parked blocks, their bytes} on the current device
+void device_parked_stats(double out[2]);
 
 template <typename T>
 class DevBuf {

@@ -682,3 +682,20 @@ def test_overlapped_analysis_equals_the_sequential_schedule(las2, oracle, monkey
     with pytest.raises(las2.SvdLibError) as ei:
         las2.svd_dim_seed(B, 5, 12345)
     assert ei.value.kind == "ImtqlbError"
+
+
+def test_device_blocks_are_parked_reused_and_given_back(las2):
+    """The allocator behind every device buffer (util.cu): a released large block is parked and handed to the next request it
+    fits (a solve repeats its sequence of sizes: no trip to the driver, no re-mapping by the stream-ordered pool); a request
+    that cannot be served next to what is parked makes the library give the parked blocks back instead of failing; trimming
+    the caches leaves nothing parked."""
+    import ctypes as C
+    from svdlibrs_b200 import _lib
+    L = _lib.lib()
+    L.svdlas2_test_device_parking.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.svdlas2_test_device_parking.restype = C.c_int
+    out = (C.c_double * 4)()
+    assert L.svdlas2_test_device_parking(-1, out) == 0, L.svdlas2_last_error()
+    assert out[0] > 8 << 20 and out[1] == 1.0 and out[2] == 1.0 and out[3] == 0.0, list(out)
+    A = sp.random(500, 300, density=0.05, format="csr", random_state=2)
+    assert las2.svd_dim_seed(A, 5, 12345).d == 5  # the library is usable afterwards
