@@ -553,7 +553,12 @@ def run_ours(args):
                 "ms_per_opb_max_over_ranks": ms_opb,
                 "spmv_b": {"GB/s": tm["bytes_spmv_b"] / tm["ms_spmv_b"] / 1e6, "ms": tm["ms_spmv_b"]},
                 "spmv_bt": {"GB/s": tm["bytes_spmv_bt"] / tm["ms_spmv_bt"] / 1e6, "ms": tm["ms_spmv_bt"]},
-                "frac_of_nominal_8TBs": ach / 8000.0}
+                "frac_of_nominal_8TBs": ach / 8000.0,
+                # what stands between `frac` and 1 (evidence under profiles/): the kernel is HBM-bound by contract, but half of
+                # this matrix's gathers are random on both sides and stay on the L1 path
+                "measured_limiter": "L1TEX tag stage: ~0.95 uncoalesced 8-byte gathers per clock per SM (2.6 from shared memory); "
+                                    "0.70 of the HBM peak needs 1.5 per clock at the sustained clock (profiles/r2g_ncu_summary.md, "
+                                    "r1_gather_microbench.md, r2u_tma_gather_microbench.md)"}
     op.close()
     # keep only what the line needs of the resident result: its 19 GB of pinned ut / vt (cfg 4) go back to the library's host
     # pool NOW, otherwise the e2e leg's results do not fit the pool's cache next to them and every e2e call would create and
