@@ -22,6 +22,10 @@ SVDLAS2_API int svdlas2_test_ql_values(uint64_t n, double *d, double *e, double 
  * here; the product replays the same plan on the GPU).  n_rotations / n_sweeps are optional outputs. */
 SVDLAS2_API int svdlas2_test_ql_vectors(uint64_t n, double *d, double *e, double *z, uint64_t *n_rotations,
                                         uint64_t *n_sweeps);
+/* The rotation plan recorded inside imtqlb (what the last analysis of T hands to ritvec) against the plan of imtql2's own
+ * recurrence on the same (d, e): returns 1 when rotations, sweeps and column permutation are bit-identical (or both fail to
+ * converge) and recording leaves imtqlb's outputs untouched, 0 when the plans differ, negative on inconsistent status codes. */
+SVDLAS2_API int svdlas2_test_ql_plans_agree(uint64_t n, const double *d, const double *e, uint64_t *n_rotations);
 /* error_bound (src/lib.rs:1480-1532): returns status; neig and the updated enough flag through pointers */
 SVDLAS2_API int svdlas2_test_refine_bounds(int *enough, double endl, double endr, double *ritz, double *bnd,
                                            uint64_t step, double tol, uint64_t *neig);

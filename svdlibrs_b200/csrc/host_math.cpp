@@ -64,7 +64,36 @@ inline size_t split_point(size_t l, size_t n, const double *d, const double *e) 
 
 } // namespace
 
-int ql_values(size_t n, double *d, double *e, double *bnd) { // src/lib.rs:962-1068
+namespace {
+
+// imtql2's final ordering (selection sort, src/lib.rs:1672-1690) applied to the eigenvalues in the order the QL iteration left
+// them; the matching column swaps of z become the plan's permutation
+void order_columns(size_t n, double *d, QlPlan &plan) {
+    for (size_t l = 1; l < n; l++) {
+        const size_t i = l - 1;
+        size_t k = i;
+        double p = d[i];
+        for (size_t j = l; j < n; j++)
+            if (d[j] < p) { k = j; p = d[j]; }
+        if (k != i) {
+            d[k] = d[i];
+            d[i] = p;
+            std::swap(plan.column_of[i], plan.column_of[k]);
+        }
+    }
+}
+
+} // namespace
+
+int ql_values(size_t n, double *d, double *e, double *bnd, QlPlan *record) { // src/lib.rs:962-1068
+    std::vector<double> unsorted; // record: d[l] as the iteration leaves it (imtqlb inserts it among d[0..l) right away)
+    if (record) {
+        record->sweeps.clear();
+        record->sc.clear();
+        record->column_of.resize(n);
+        for (size_t k = 0; k < n; k++) record->column_of[k] = (uint32_t)k;
+        unsorted.assign(d, d + n);
+    }
     if (n == 1) return SVDLAS2_OK;
     const size_t last = n - 1;
     bnd[0] = 1.0;
@@ -80,6 +109,7 @@ int ql_values(size_t n, double *d, double *e, double *bnd) { // src/lib.rs:962-1
             double p = d[l];
             double f = bnd[l];
             if (m == l) {
+                if (record) unsorted[l] = p;
                 // d[l] has converged: insert it (and its bound) among the already ordered d[0..l)
                 size_t pos = l;
                 while (pos >= 1 && p < d[pos - 1]) {
@@ -102,6 +132,7 @@ int ql_values(size_t n, double *d, double *e, double *bnd) { // src/lib.rs:962-1
             if (m == 0) return SVDLAS2_ERR_REFERENCE_PANIC; // src/lib.rs:1029
             size_t i = m - 1;
             bool underflow = false;
+            QlSweep sw{(uint32_t)i, 0, record ? (uint64_t)(record->sc.size() / 2) : 0};
             for (;;) {
                 f = s * e[i];
                 const double b = c * e[i];
@@ -118,9 +149,15 @@ int ql_values(size_t n, double *d, double *e, double *bnd) { // src/lib.rs:962-1
                 f = bnd[i + 1];
                 bnd[i + 1] = s * bnd[i] + c * f;
                 bnd[i] = c * bnd[i] - s * f;
+                if (record) { // the rotation imtql2 would apply to columns (i, i+1) of z at this point (:1646-1652)
+                    record->sc.push_back(s);
+                    record->sc.push_back(c);
+                    sw.count++;
+                }
                 if (i == l) break; // covers both `i == 0` and the loop condition `i >= l`
                 i--;
             }
+            if (record && sw.count) record->sweeps.push_back(sw);
             if (underflow) {
                 d[i + 1] -= p;
             } else {
@@ -130,6 +167,7 @@ int ql_values(size_t n, double *d, double *e, double *bnd) { // src/lib.rs:962-1
             e[m] = 0.0;
         }
     }
+    if (record) order_columns(n, unsorted.data(), *record);
     return SVDLAS2_OK;
 }
 
@@ -188,19 +226,7 @@ int ql_rotations(size_t n, double *d, double *e, QlPlan &plan) { // src/lib.rs:1
             e[m] = 0.0;
         }
     }
-    // order the eigenvalues (selection sort); the matching column swaps of z become a permutation
-    for (size_t l = 1; l < n; l++) {
-        const size_t i = l - 1;
-        size_t k = i;
-        double p = d[i];
-        for (size_t j = l; j < n; j++)
-            if (d[j] < p) { k = j; p = d[j]; }
-        if (k != i) {
-            d[k] = d[i];
-            d[i] = p;
-            std::swap(plan.column_of[i], plan.column_of[k]);
-        }
-    }
+    order_columns(n, d, plan);
     return SVDLAS2_OK;
 }
 

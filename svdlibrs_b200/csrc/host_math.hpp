@@ -35,7 +35,12 @@ size_t argmax_abs(size_t n, const double *x);
 void cosort_ascending(size_t n, double *keys, double *vals);
 
 // status: 0 ok, SVDLAS2_ERR_IMTQLB, SVDLAS2_ERR_REFERENCE_PANIC
-int ql_values(size_t n, double *d, double *e, double *bnd);
+// record != nullptr: also records the rotation plan imtql2 would produce for the SAME (d, e).  The implicit-QL iterations of
+// imtqlb and imtql2 are the same recurrences on the same data (imtqlb merely files every converged eigenvalue among d[0..l)
+// at once, positions the iteration never reads again, where imtql2 sorts at the end), so the plan is bit-identical to
+// ql_rotations' (tests/test_host_logic.py) and ritvec need not run the O(n^2) chain a second time when T is one block.
+struct QlPlan;
+int ql_values(size_t n, double *d, double *e, double *bnd, QlPlan *record = nullptr);
 
 // One Givens rotation of columns (i, i+1) of z:  f = z[i+1]; z[i+1] = s*z[i] + c*f; z[i] = c*z[i] - s*f
 struct QlSweep {

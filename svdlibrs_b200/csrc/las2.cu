@@ -470,7 +470,11 @@ struct Solver {
             const u64 sz = i - l;
             for (u64 k = 0; k <= sz; k++) ritz[l + sz - k] = alf[l + k];     // svd_dcopy reverses, :1985
             for (u64 k = 0; k < sz; k++) w5[l + 1 + (sz - 1) - k] = betv[l + 1 + k]; // :1986
-            int rc = ql_values(sz + 1, &ritz[l], &w5[l], &bnd[l]);
+            // T in one unreduced block: this is the very iteration imtql2 will run on T if the analysis turns out to be the last
+            // one, so its rotations are kept for ritvec
+            const bool whole = l == 0 && sz == j;
+            int rc = ql_values(sz + 1, &ritz[l], &w5[l], &bnd[l], whole ? &kept_plan : nullptr);
+            kept_plan_js = (whole && rc == 0) ? j + 1 : 0;
             if (rc == SVDLAS2_ERR_IMTQLB)
                 throw Error(rc, "imtqlb no convergence to an eigenvalue after 30 iterations");
             if (rc) throw Error(rc, "imtqlb: expected 'm' to be non-zero");
@@ -484,6 +488,8 @@ struct Solver {
         *neig = ne;
     }
     double endl_ = 0.0, endr_ = 0.0;
+    QlPlan kept_plan;      // rotation plan of the latest analysis (valid for T of order kept_plan_js; 0: none)
+    u64 kept_plan_js = 0;
 
     // the batch scheduler (:1996-2009): returns the next `last`, or sets *enough
     u64 next_last(u64 first, u64 j, u64 neig, u64 *intro, bool *enough) const {
@@ -702,9 +708,16 @@ struct Solver {
 
         const double tq0 = wall();
         QlPlan plan;
-        int rc = ql_rotations(js, dd.data(), ee.data(), plan);
-        if (rc == SVDLAS2_ERR_IMTQL2) throw Error(rc, "imtql2 no convergence to an eigenvalue after 30 iterations");
-        if (rc) throw Error(rc, "imtql2: expected 'm' to be non-zero");
+        static const bool reuse_on = [] { const char *e = std::getenv("SVDLAS2_REUSE_QL_PLAN"); return !(e && e[0] == '0'); }();
+        const bool reused = reuse_on && kept_plan_js == js;
+        if (reused) {
+            plan = std::move(kept_plan); // the last analysis ran this very iteration on this very T (host_math.hpp)
+            kept_plan_js = 0;
+        } else {
+            int rc = ql_rotations(js, dd.data(), ee.data(), plan);
+            if (rc == SVDLAS2_ERR_IMTQL2) throw Error(rc, "imtql2 no convergence to an eigenvalue after 30 iterations");
+            if (rc) throw Error(rc, "imtql2: expected 'm' to be non-zero");
+        }
         const double tq1 = wall();
         const u32 ldz = (u32)round_up(js, 32);
         DevBuf<double> zT((size_t)ldz * js);
@@ -712,9 +725,9 @@ struct Solver {
         LAS2_CUDA(cudaStreamSynchronize(s));
         *t_imtql2 = wall() - tq0;
         if (std::getenv("SVDLAS2_TRACE"))
-            fprintf(stderr, "[svdlas2] imtql2: js=%llu rotations=%llu sweeps=%zu host %.4f s, device replay %.4f s\n",
+            fprintf(stderr, "[svdlas2] imtql2: js=%llu rotations=%llu sweeps=%zu host %.4f s%s, device replay %.4f s\n",
                     (unsigned long long)js, (unsigned long long)plan.rotations(), plan.sweeps.size(), tq1 - tq0,
-                    wall() - tq1);
+                    reused ? " (plan of the last analysis reused)" : "", wall() - tq1);
 
         // acceptance (:1800-1801) in ascending eigenvalue order; the reference's circular buffer + rotate_array
         // keep the LAST `dims` accepted, largest first (:1802-1827)

@@ -1,6 +1,7 @@
 // testing_abi.cpp -- include/svdlas2_testing.h: host-logic hooks for the CPU test-suite.
 #include "../../include/svdlas2_testing.h"
 
+#include <cstring>
 #include <vector>
 
 #include "host_math.hpp"
@@ -46,6 +47,27 @@ int svdlas2_test_ql_vectors(uint64_t n, double *d, double *e, double *z, uint64_
     for (uint64_t row = 0; row < n; row++)
         for (uint64_t k = 0; k < n; k++) z[row * n + k] = zp[row * n + plan.column_of[k]];
     return 0;
+}
+
+int svdlas2_test_ql_plans_agree(uint64_t n, const double *d, const double *e, uint64_t *n_rotations) {
+    // imtqlb with recording against imtql2's own recurrence, on copies of the same (d, e)
+    std::vector<double> d1(d, d + n), e1(e, e + n), b1(n, 1.7976931348623157e308), d2(d, d + n), e2(e, e + n);
+    std::vector<double> d0(d, d + n), e0(e, e + n), b0(n, 1.7976931348623157e308);
+    QlPlan rec, ref;
+    const int rc0 = ql_values(n, d0.data(), e0.data(), b0.data());
+    const int rc1 = ql_values(n, d1.data(), e1.data(), b1.data(), &rec);
+    const int rc2 = ql_rotations(n, d2.data(), e2.data(), ref);
+    if (n_rotations) *n_rotations = ref.rotations();
+    if (rc0 != rc1) return -1;
+    if (rc1 != 0 || rc2 != 0) return (rc1 != 0 && rc2 != 0) ? 1 : -2; // both fail to converge, or they disagree
+    // recording must not change what imtqlb returns
+    if (std::memcmp(d0.data(), d1.data(), n * sizeof(double)) || std::memcmp(b0.data(), b1.data(), n * sizeof(double))) return -3;
+    if (rec.sc.size() != ref.sc.size() || rec.sweeps.size() != ref.sweeps.size() || rec.column_of != ref.column_of) return 0;
+    if (!rec.sc.empty() && std::memcmp(rec.sc.data(), ref.sc.data(), rec.sc.size() * sizeof(double))) return 0;
+    for (size_t k = 0; k < rec.sweeps.size(); k++)
+        if (rec.sweeps[k].hi != ref.sweeps[k].hi || rec.sweeps[k].count != ref.sweeps[k].count || rec.sweeps[k].first != ref.sweeps[k].first)
+            return 0;
+    return 1;
 }
 
 int svdlas2_test_refine_bounds(int *enough, double endl, double endr, double *ritz, double *bnd, uint64_t step,

@@ -26,6 +26,8 @@ def hooks(las2):
     L.svdlas2_test_refine_bounds.restype = C.c_int
     L.svdlas2_test_cosort.argtypes = [C.c_uint64, f64p, f64p]
     L.svdlas2_test_cosort.restype = None
+    L.svdlas2_test_ql_plans_agree.argtypes = [C.c_uint64, f64p, f64p, C.POINTER(C.c_uint64)]
+    L.svdlas2_test_ql_plans_agree.restype = C.c_int
     L.svdlas2_test_host_block.argtypes = [C.c_uint64, C.POINTER(C.c_int)]
     L.svdlas2_test_host_block.restype = C.c_int
     return L
@@ -154,3 +156,33 @@ def test_host_result_block_without_a_device(hooks, nbytes):
     node = C.c_int(-7)
     assert hooks.svdlas2_test_host_block(nbytes, C.byref(node)) == 0
     assert node.value >= -1
+
+
+@pytest.mark.parametrize("n,seed,clustered", [(1, 0, False), (2, 0, False), (3, 1, False), (17, 2, False), (64, 3, False),
+                                               (64, 4, True), (200, 5, False), (500, 6, False), (500, 7, True), (1200, 8, False)])
+def test_plan_recorded_by_the_last_analysis_is_imtql2s_plan(hooks, n, seed, clustered):
+    """ritvec reuses the rotations the final analysis of T recorded inside imtqlb (src/lib.rs:962-1068) instead of running
+    imtql2's recurrence (:1576-1645) again on the same T: the two plans must be bit-identical -- rotations, sweeps and the
+    column permutation of the final ordering -- and recording must not change imtqlb's own outputs."""
+    d, e = tridiag(n, seed, clustered)
+    nrot = C.c_uint64()
+    assert hooks.svdlas2_test_ql_plans_agree(n, p(d), p(e), C.byref(nrot)) == 1
+    assert nrot.value >= max(0, n - 1)
+
+
+def test_plan_recording_with_split_and_degenerate_tridiagonals(hooks):
+    """zeros on the off-diagonal (T splits inside the iteration), repeated eigenvalues, NaN (both recurrences give up)"""
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        n = int(rng.integers(2, 90))
+        d = rng.standard_normal(n)
+        e = np.concatenate(([0.0], np.abs(rng.standard_normal(n - 1))))
+        if trial % 4 == 0:
+            e[rng.integers(1, n)] = 0.0
+        if trial % 4 == 1:
+            d[:] = 1.0
+        if trial % 4 == 2:
+            e[1:] *= 1e-9
+        assert hooks.svdlas2_test_ql_plans_agree(n, p(d), p(e), None) == 1, (trial, n)
+    d, e = np.array([1.0, np.nan, 2.0]), np.array([0.0, 0.5, 0.5])
+    assert hooks.svdlas2_test_ql_plans_agree(3, p(d), p(e), None) == 1
