@@ -15,15 +15,21 @@
 // Scalars (alf, bet, rnm, reorthogonalisation coefficients) are produced as per-CTA partials, consumed on the
 // device by the next kernel of the chain, and read back ONCE per Lanczos step (one extra time per purge pass)
 // for the host-side recurrences (ortbnd, the purge trigger, tol).
+//
+// How a step is launched: large operators -- the SpMV pair of opb (chunk_spmv.cu; sharded: + the exchange kernel of
+// peer_ring.cu), then either the chain of k_axpy_dot kernels or ONE k_step_chain launch (vectors of up to 8 MB); small operators
+// in plain CSR on one GPU -- the whole step incl. both SpMVs as one k_step_chain<true> launch (vecops.cuh, StepSpmv).
+// Host recurrences: the analyses of T run imtqlb; the last one also records imtql2's rotation plan, which ritvec replays on
+// the GPU (tridiag_device.cu) without running the O(js^2) chain again.
 #include "las2.hpp"
 
-#include <chrono>
 #include <atomic>
+#include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <future>
 #include <mutex>
 #include <thread>
-#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
