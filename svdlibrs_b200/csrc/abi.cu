@@ -129,6 +129,7 @@ int svdlas2_trim_caches(void) {
     return guarded([&] {
         host_pool_trim();
         device_pool_trim();
+        plan_cache_trim();
     });
 }
 

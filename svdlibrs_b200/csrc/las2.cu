@@ -56,6 +56,18 @@ double wall() {
 
 u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
+// The rotation plan an analysis records is O(js^2) doubles (86 MB at js 2252); growing a fresh vector to that size costs more
+// than the recording itself (page faults + reallocation copies: +0.13 s at cfg 5, measured on the host alone), so one spare
+// plan's storage is kept per process between solves, like the result and device buffers (svdlas2_trim_caches() drops it).
+struct PlanSpare {
+    std::mutex mu;
+    QlPlan plan;
+};
+PlanSpare &plan_spare() {
+    static PlanSpare *p = new PlanSpare(); // leaked on purpose, like the other caches
+    return *p;
+}
+
 struct Solver {
     Operator &op;
     cudaStream_t s;
@@ -96,6 +108,12 @@ struct Solver {
         : op(o), s(o.stream), N(o.N), M(o.M), ld(round_up(o.N, 32)), dims(dimensions), iters(iterations),
           eps1(kEps * std::sqrt((double)o.N)) {
         std::memset(&prof, 0, sizeof prof);
+        {
+            PlanSpare &ps = plan_spare();
+            std::lock_guard<std::mutex> lk(ps.mu);
+            kept_plan = std::move(ps.plan);
+            ps.plan = QlPlan();
+        }
         if (op.ring) { r.p = op.ring->r_mine(); } else { r_own.alloc(ld); r.p = r_own.get(); }
         xs.alloc(ld); t.alloc(M ? M : 1);
         LAS2_CUDA(cudaMemsetAsync(r.get(), 0, ld * sizeof(double), s));
@@ -150,6 +168,11 @@ struct Solver {
         }
     }
     ~Solver() {
+        {
+            PlanSpare &ps = plan_spare();
+            std::lock_guard<std::mutex> lk(ps.mu);
+            if (kept_plan.sc.capacity() > ps.plan.sc.capacity()) ps.plan = std::move(kept_plan);
+        }
         for (auto &e : opb_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         // buffers nobody took (an error before ritvec) go back to the pool
@@ -479,6 +502,12 @@ struct Solver {
             // T in one unreduced block: this is the very iteration imtql2 will run on T if the analysis turns out to be the last
             // one, so its rotations are kept for ritvec
             const bool whole = l == 0 && sz == j;
+            if (whole) {
+                // ~1.1 (j+1)^2 rotations; make room before recording (the vector is empty here: no copy), geometrically
+                const size_t need = (size_t)(2.6 * (double)(j + 1) * (double)(j + 1)) + 64;
+                kept_plan.sc.clear();
+                if (kept_plan.sc.capacity() < need) kept_plan.sc.reserve(std::max(need, 2 * kept_plan.sc.capacity()));
+            }
             int rc = ql_values(sz + 1, &ritz[l], &w5[l], &bnd[l], whole ? &kept_plan : nullptr);
             kept_plan_js = (whole && rc == 0) ? j + 1 : 0;
             if (rc == SVDLAS2_ERR_IMTQLB)
@@ -713,14 +742,14 @@ struct Solver {
         for (u64 i = 0; i < steps; i++) ee[1 + (steps - 1) - i] = bet[1 + i];  // svd_dcopy(steps, 1, bet, w5), :1791
 
         const double tq0 = wall();
-        QlPlan plan;
+        QlPlan own_plan;
         static const bool reuse_on = [] { const char *e = std::getenv("SVDLAS2_REUSE_QL_PLAN"); return !(e && e[0] == '0'); }();
         const bool reused = reuse_on && kept_plan_js == js;
-        if (reused) {
-            plan = std::move(kept_plan); // the last analysis ran this very iteration on this very T (host_math.hpp)
-            kept_plan_js = 0;
-        } else {
-            int rc = ql_rotations(js, dd.data(), ee.data(), plan);
+        // (reused: the last analysis ran this very iteration on this very T, host_math.hpp; the plan stays where it is so
+        // that its storage serves the next solve)
+        const QlPlan &plan = reused ? kept_plan : own_plan;
+        if (!reused) {
+            int rc = ql_rotations(js, dd.data(), ee.data(), own_plan);
             if (rc == SVDLAS2_ERR_IMTQL2) throw Error(rc, "imtql2 no convergence to an eigenvalue after 30 iterations");
             if (rc) throw Error(rc, "imtql2: expected 'm' to be non-zero");
         }
@@ -944,6 +973,12 @@ void Operator::opb_step(const double *x, const double *qprev, double rnm, double
         vec_axpy_dot(r, qprev, Coef::value(rnm), x, ld, *alf, stream);
         if (launches) *launches += 1;
     }
+}
+
+void plan_cache_trim() {
+    PlanSpare &ps = plan_spare();
+    std::lock_guard<std::mutex> lk(ps.mu);
+    ps.plan = QlPlan();
 }
 
 void solve(Operator &op, u64 dimensions, u64 iterations, const double end_interval[2], double kappa,

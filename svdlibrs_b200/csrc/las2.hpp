@@ -58,6 +58,9 @@ struct Operator {
     void opb_step(const double *x, const double *qprev, double rnm, double *r, double *t, PartialSlot *alf, u64 ld, u64 *launches);
 };
 
+// drops the process-wide spare storage of imtql2's rotation plan (svdlas2_trim_caches)
+void plan_cache_trim();
+
 struct SolveOutput; // svdlas2_result with owned buffers (abi.cu)
 
 // svdLAS2 (src/lib.rs:570-655) on a resident operator; fills *res (already calloc'ed). Throws las2::Error.
