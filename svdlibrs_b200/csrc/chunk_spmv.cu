@@ -47,7 +47,7 @@ namespace {
 
 // launch shapes: (warps per CTA, stages per warp).  Both fill 96 KB of shared memory with stages.  16 x 2 hides the
 // bulk-copy latency inside each warp; 32 x 1 doubles the warps that hide each other's ALU / shuffle latencies (the
-// slab mode is latency-bound: 41 % issue-active with 4 warps per scheduler, profiles/r1g).
+// slab mode is latency-bound: 41 % issue-active with 4 warps per scheduler, profiles/r1_spmv_iterations.md).
 constexpr int kChunkStageBytesTotal = 32 * kChunkBytes;
 constexpr u32 kChunkHotMax = 8192; // doubles of x kept in shared memory at most (64 KB)
 constexpr u32 kChunkHotDefault = 8192; // cfg 2, B: 0.116 ms with 8192 entries, 0.122 ms with 4096

@@ -332,7 +332,7 @@ k_ritz_contract(const double *__restrict__ Q, u64 ld, u32 js, const double *__re
 // V[rows, c0 .. c0+64) = Q[rows, 0 .. js) . C[0 .. js, c0 .. c0+64) for a block of 128 rows: 8 warps, each a 32 x 32 tile of
 // 4 x 4 mma tiles (32 accumulators per thread); the 128 x 16 slice of Q and the 16 x 64 slice of C of every k-step are staged
 // in shared memory (double-buffered, cp.async), so a row block of Q is read d / 64 times instead of d / 8 (k_ritz_contract re-reads
-// the panel 125 times at d = 1000 and is bandwidth-bound on exactly that, profiles/r2_ritz_ncu_summary.md).  Row padding of 4
+// the panel 125 times at d = 1000 and is bandwidth-bound on exactly that, profiles/r2g_ncu_summary.md section 2).  Row padding of 4
 // doubles makes both fragment reads conflict-free.  The accumulation order is fixed (k ascending, 4 products per instruction).
 constexpr int kDmTM = 128, kDmTN = 64, kDmTK = 16, kDmThreads = 256;
 constexpr int kDmLdA = kDmTM + 4, kDmLdB = kDmTN + 4;
