@@ -29,6 +29,7 @@
 #include <condition_variable>
 #include <future>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -501,12 +502,17 @@ struct Solver {
             for (u64 k = 0; k < sz; k++) w5[l + 1 + (sz - 1) - k] = betv[l + 1 + k]; // :1986
             // T in one unreduced block: this is the very iteration imtql2 will run on T if the analysis turns out to be the last
             // one, so its rotations are kept for ritvec
-            const bool whole = l == 0 && sz == j;
+            bool whole = l == 0 && sz == j;
             if (whole) {
-                // ~1.1 (j+1)^2 rotations; make room before recording (the vector is empty here: no copy), geometrically
-                const size_t need = (size_t)(2.6 * (double)(j + 1) * (double)(j + 1)) + 64;
+                // ~1.1 (j+1)^2 rotations; make room before recording (the vector is empty here: no copy), geometrically, and
+                // never more than 1 GB ahead of need (beyond that the vector grows on demand, as ql_rotations' own would)
+                const size_t need = std::min<size_t>((size_t)(2.6 * (double)(j + 1) * (double)(j + 1)) + 64, (size_t)1 << 27);
                 kept_plan.sc.clear();
-                if (kept_plan.sc.capacity() < need) kept_plan.sc.reserve(std::max(need, 2 * kept_plan.sc.capacity()));
+                try {
+                    if (kept_plan.sc.capacity() < need) kept_plan.sc.reserve(std::max(need, 2 * kept_plan.sc.capacity()));
+                } catch (const std::bad_alloc &) {
+                    whole = false; // no room for a plan now: ritvec will run imtql2's recurrence itself
+                }
             }
             int rc = ql_values(sz + 1, &ritz[l], &w5[l], &bnd[l], whole ? &kept_plan : nullptr);
             kept_plan_js = (whole && rc == 0) ? j + 1 : 0;
